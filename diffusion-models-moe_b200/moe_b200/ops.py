@@ -1,0 +1,186 @@
+"""Thin tensor -> pointer wrappers over the C ABI.  Every function enqueues on the current
+CUDA stream of the tensors' device and returns without synchronising."""
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+ACT_GELU = 0
+ACT_RELU = 1
+
+
+def _ptr(t: Optional[torch.Tensor]) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _need(t: torch.Tensor, dtype, name: str, shape=None) -> None:
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (no CPU fallback exists for this path)")
+    if t.dtype != dtype:
+        raise ValueError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise ValueError(f"{name} must have shape {tuple(shape)}, got {tuple(t.shape)}")
+
+
+def launch_count() -> int:
+    return int(_lib.load().moe_launch_count())
+
+
+def reset_launch_count() -> None:
+    _lib.load().moe_reset_launch_count()
+
+
+def geglu_up(x, w1p, b1p, n_experts: int, expert_size: int, act: int = ACT_GELU, *, neuron_override=None,
+             override_value: float = -0.17, want_scores: bool = True, want_gate: bool = False, out=None,
+             scores_out=None):
+    """K1.  x bf16 [T, d]; w1p bf16 [2h, d] packed; b1p f32 [2h] or None.
+    Returns (H bf16 [T, h], scores f32 [T, E] | None, gate bf16 [T, h] | None)."""
+    lib = _lib.load()
+    T, d = x.shape
+    h = w1p.shape[0] // 2
+    _need(x, torch.bfloat16, "x")
+    _need(w1p, torch.bfloat16, "w1p", (2 * h, d))
+    if b1p is not None:
+        _need(b1p, torch.float32, "b1p", (2 * h,))
+    if neuron_override is not None:
+        _need(neuron_override, torch.uint8, "neuron_override", (h,))
+    H = out if out is not None else torch.empty((T, h), dtype=torch.bfloat16, device=x.device)
+    _need(H, torch.bfloat16, "out", (T, h))
+    scores = None
+    if want_scores:
+        scores = scores_out if scores_out is not None else torch.empty((T, n_experts), dtype=torch.float32,
+                                                                       device=x.device)
+        _need(scores, torch.float32, "scores_out", (T, n_experts))
+    gate = torch.empty((T, h), dtype=torch.bfloat16, device=x.device) if want_gate else None
+    with torch.cuda.device(x.device):
+        rc = lib.moe_geglu_up(_ptr(x), _ptr(w1p), _ptr(b1p), _ptr(neuron_override), float(override_value), _ptr(H),
+                              _ptr(scores), _ptr(gate), T, d, h, n_experts, expert_size, act, _stream(x))
+    _lib.check(rc, "moe_geglu_up")
+    return H, scores, gate
+
+
+def router_topk(scores, k: int, *, removed_bits=None, want_bits: bool = True, want_idx: bool = False, hist=None,
+                colmax_out=None, H=None, expert_size: int = 0, count_rows=(0, 0), bits_out=None):
+    """K2.  scores f32 [T, E].  Returns (active_bits i32 [T, W] | None, idx i16 [T, k] | None).
+    `hist` (int64 [E]) and `colmax_out` (f32 [E], pre-filled with -inf) are accumulated in place;
+    `H` (bf16 [T, E*expert_size]) is zeroed in place for inactive experts."""
+    lib = _lib.load()
+    _need(scores, torch.float32, "scores")
+    T, E = scores.shape
+    W = (E + 31) // 32
+    dev = scores.device
+    if removed_bits is not None:
+        _need(removed_bits, torch.int32, "removed_bits", (W,))
+    bits = None
+    if want_bits:
+        bits = bits_out if bits_out is not None else torch.empty((T, W), dtype=torch.int32, device=dev)
+        _need(bits, torch.int32, "bits_out", (T, W))
+    idx = torch.empty((T, k), dtype=torch.int16, device=dev) if want_idx else None
+    if hist is not None:
+        _need(hist, torch.int64, "hist", (E,))
+    if colmax_out is not None:
+        _need(colmax_out, torch.float32, "colmax_out", (E,))
+    h = 0
+    if H is not None:
+        h = E * expert_size
+        _need(H, torch.bfloat16, "H", (T, h))
+    with torch.cuda.device(dev):
+        rc = lib.moe_router_topk(_ptr(scores), _ptr(removed_bits), int(k), _ptr(bits), _ptr(idx), _ptr(hist),
+                                 _ptr(colmax_out), _ptr(H), h, int(expert_size), T, E, int(count_rows[0]),
+                                 int(count_rows[1]), _stream(scores))
+    _lib.check(rc, "moe_router_topk")
+    return bits, idx
+
+
+def down_proj(H, w2p, b2, out=None):
+    """K3.  H bf16 [T, h]; w2p bf16 [d, h]; b2 f32 [d] or None -> Y bf16 [T, d]."""
+    lib = _lib.load()
+    T, h = H.shape
+    d = w2p.shape[0]
+    _need(H, torch.bfloat16, "H")
+    _need(w2p, torch.bfloat16, "w2p", (d, h))
+    if b2 is not None:
+        _need(b2, torch.float32, "b2", (d,))
+    Y = out if out is not None else torch.empty((T, d), dtype=torch.bfloat16, device=H.device)
+    _need(Y, torch.bfloat16, "out", (T, d))
+    with torch.cuda.device(H.device):
+        rc = lib.moe_down_proj(_ptr(H), _ptr(w2p), _ptr(b2), _ptr(Y), T, h, d, _stream(H))
+    _lib.check(rc, "moe_down_proj")
+    return Y
+
+
+def hist_accumulate(idx, n_experts: int, hist=None):
+    """K4.  idx int16 (any shape) -> hist int64 [E] (accumulated in place if given)."""
+    lib = _lib.load()
+    _need(idx, torch.int16, "idx")
+    if hist is None:
+        hist = torch.zeros(n_experts, dtype=torch.int64, device=idx.device)
+    _need(hist, torch.int64, "hist", (n_experts,))
+    with torch.cuda.device(idx.device):
+        rc = lib.moe_hist_accumulate(_ptr(idx), idx.numel(), n_experts, _ptr(hist), _stream(idx))
+    _lib.check(rc, "moe_hist_accumulate")
+    return hist
+
+
+def colmax(m, out=None):
+    """Column max over rows of a [T, C] f32 / bf16 matrix, max-accumulated into out (f32 [C])."""
+    lib = _lib.load()
+    if m.dtype not in (torch.float32, torch.bfloat16):
+        raise ValueError("colmax: f32 or bf16 only")
+    _need(m, m.dtype, "m")
+    T, C = m.shape
+    if out is None:
+        out = torch.full((C,), float("-inf"), dtype=torch.float32, device=m.device)
+    _need(out, torch.float32, "out", (C,))
+    fn = lib.moe_colmax_f32 if m.dtype == torch.float32 else lib.moe_colmax_bf16
+    with torch.cuda.device(m.device):
+        rc = fn(_ptr(m), T, C, _ptr(out), _stream(m))
+    _lib.check(rc, "moe_colmax")
+    return out
+
+
+def mask_pack(dense):
+    """dense uint8 0/1 (any shape, n elements) -> int32 [ceil(n/32)] bit words (bit i%32 of word i/32)."""
+    lib = _lib.load()
+    _need(dense, torch.uint8, "dense")
+    n = dense.numel()
+    bits = torch.empty(((n + 31) // 32,), dtype=torch.int32, device=dense.device)
+    with torch.cuda.device(dense.device):
+        rc = lib.moe_mask_pack(_ptr(dense), n, _ptr(bits), _stream(dense))
+    _lib.check(rc, "moe_mask_pack")
+    return bits
+
+
+def mask_union(a, b, out=None):
+    lib = _lib.load()
+    _need(a, torch.int32, "a")
+    _need(b, torch.int32, "b", a.shape)
+    if out is None:
+        out = torch.empty_like(a)
+    _need(out, torch.int32, "out", a.shape)
+    with torch.cuda.device(a.device):
+        rc = lib.moe_mask_union(_ptr(a), _ptr(b), _ptr(out), a.numel(), _stream(a))
+    _lib.check(rc, "moe_mask_union")
+    return out
+
+
+def mask_weights(w2, bits, out=None):
+    """w2 bf16 [d, h]; bits int32 [d*h/32] -> masked copy (element zeroed where its bit is set)."""
+    lib = _lib.load()
+    d, h = w2.shape
+    _need(w2, torch.bfloat16, "w2")
+    _need(bits, torch.int32, "bits", (d * h // 32,))
+    if out is None:
+        out = torch.empty_like(w2)
+    _need(out, torch.bfloat16, "out", (d, h))
+    with torch.cuda.device(w2.device):
+        rc = lib.moe_mask_weights(_ptr(w2), _ptr(bits), _ptr(out), d, h, _stream(w2))
+    _lib.check(rc, "moe_mask_weights")
+    return out

@@ -1,0 +1,137 @@
+/*
+ * moe_b200.h -- C ABI of libmoe_b200.so: the B200 (sm_100a) implementation of the MoEfied
+ * GEGLU feed-forward hot path of ruchikachavhan/diffusion-models-moe.
+ *
+ * The reference has no FFI of its own (it is pure Python calling ATen from torch forward
+ * hooks), so each entry point below names the reference hook code it replaces
+ * (paths relative to the reference root).  INTEGRATION.md shows the ctypes stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch) unless marked host;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing syncs;
+ *   - return value: 0 = ok, <0 = error (MOE_ERR_*); moe_last_error() gives the message of the
+ *     last failing call on the calling thread;
+ *   - bf16 tensors are row-major contiguous; "packed" neuron order means the inner (h)
+ *     dimension has been permuted so that expert e owns neurons [e*es, (e+1)*es)
+ *     (moe_b200.packing / helper.modify_ffn_to_experts do this once per model);
+ *   - T = B*S tokens, d = model dim, h = GEGLU inner dim, E experts of es neurons (E*es == h),
+ *     W = ceil(E/32) 32-bit words per token for expert bit sets (bit e%32 of word e/32).
+ */
+#ifndef MOE_B200_H
+#define MOE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define MOE_API __attribute__((visibility("default")))
+#else
+#define MOE_API
+#endif
+
+#define MOE_OK 0
+#define MOE_ERR_INVALID_ARGUMENT (-1)
+#define MOE_ERR_UNSUPPORTED_SHAPE (-2)
+#define MOE_ERR_CUDA (-3)
+#define MOE_ERR_NO_DEVICE (-4)
+
+#define MOE_ACT_GELU 0 /* exact erf GELU (upstream diffusers GEGLU.gelu) */
+#define MOE_ACT_RELU 1 /* sparsity/relufy_model.py:28-40 */
+
+/* ABI version; bumped whenever a signature changes. */
+MOE_API int moe_abi_version(void);
+/* Message of the last error on this thread ("" if none). Host pointer, valid until the next call. */
+MOE_API const char* moe_last_error(void);
+/* Number of kernels this library has launched since load / since the last reset (bench bookkeeping). */
+MOE_API long long moe_launch_count(void);
+MOE_API void moe_reset_launch_count(void);
+
+/*
+ * K1 -- GEGLU up-projection with the gate activation, the per-neuron override and the
+ * per-expert score segment-sum fused into the epilogue (tcgen05 / TMEM / TMA).
+ *
+ *   Y = x W1p^T + b1p;  v = Y[:, 0:h], g = act(Y[:, h:2h]);  g[:, n] = override_value where
+ *   neuron_override[n] != 0;  scores[t, e] = sum_{n in expert e} g[t, n];  H = v * g.
+ *
+ * Replaces: neuron_receivers/moefy.py:11-13,18-20 (module.proj, chunk, module.gelu,
+ * matmul(gate, patterns^T)); remove_skilled_neurons.py:30-42 (override = -0.17);
+ * expert_activation.py:48-56; frequency_measure.py:44-51.
+ *
+ *   x      bf16 [T, d]        w1p  bf16 [2h, d]  (value rows first, then gate rows; packed order)
+ *   b1p    f32  [2h] or NULL  neuron_override u8 [h] or NULL
+ *   H      bf16 [T, h] out    scores f32 [T, E] out or NULL     gate_out bf16 [T, h] out or NULL
+ * Constraints: d % 8 == 0, h % 8 == 0, E*es == h; the tile width is chosen from es
+ * (lcm(es,8)-multiples); unsupported geometries return MOE_ERR_UNSUPPORTED_SHAPE.
+ */
+MOE_API int moe_geglu_up(const void* x, const void* w1p, const float* b1p, const uint8_t* neuron_override,
+                 float override_value, void* H, float* scores, void* gate_out, int T, int d, int h, int E,
+                 int es, int act, void* stream);
+
+/*
+ * K2 -- router: per-token top-k select over E expert scores (one warp per token, radix select
+ * on order-preserving keys, ties to the lower expert id), fused with the selection histogram,
+ * the score column-max and the in-place zeroing of H for unselected / removed experts.
+ *
+ * Replaces: moefy.py:21-23 (topk, embedding(labels, patterns).sum, gate[mask==0]=0);
+ * frequency_measure.py:52-57 (Python counter loop; integer counts instead of += 1/S);
+ * remove_skilled_experts.py:29-49 (removed experts score exactly 0, still compete, own no
+ * neurons); expert_activation.py:57 (max over tokens).
+ *
+ *   scores        f32 [T, E]
+ *   removed_bits  u32 [W] or NULL: experts whose pattern row is zeroed for this (timestep, layer)
+ *   active_bits   u32 [T, W] out or NULL: selected AND NOT removed (what owns live neurons)
+ *   idx           i16 [T, k] out or NULL: selected expert ids, ascending (includes removed ones
+ *                 that took a slot, exactly as the reference's `labels`)
+ *   hist          u64 [E] accumulated (+= 1 per (token, selected expert)) for tokens in
+ *                 [count_begin, count_end), or NULL
+ *   score_colmax  f32 [E] max-accumulated over all T tokens (caller pre-fills with -inf), or NULL
+ *   H             bf16 [T, h] zeroed in place where the neuron's expert is not active, or NULL
+ */
+MOE_API int moe_router_topk(const float* scores, const uint32_t* removed_bits, int k, uint32_t* active_bits,
+                    int16_t* idx, unsigned long long* hist, float* score_colmax, void* H, int h, int es,
+                    int T, int E, int count_begin, int count_end, void* stream);
+
+/*
+ * K3 -- down-projection Y = H W2p^T + b2 (tcgen05 / TMEM / TMA).  H has already been zeroed
+ * for inactive experts by K2, so this is the dense-masked form; W2p may be the
+ * Wanda-masked copy produced by moe_mask_weights.
+ * Replaces: upstream FeedForward.net[2] (Linear(h, d)) and
+ * remove_wanda_neurons_fast.py:69-83 (F.linear(x, W2*(1-M), b2)).
+ *   H bf16 [T, h]   w2p bf16 [d, h] (columns in packed order)   b2 f32 [d] or NULL   Y bf16 [T, d] out
+ */
+MOE_API int moe_down_proj(const void* H, const void* w2p, const float* b2, void* Y, int T, int h, int d,
+                  void* stream);
+
+/*
+ * K4 -- standalone expert-frequency histogram over stored labels:
+ * hist[e] += #occurrences of e in idx[0:n] (vectorised loads, warp-aggregated shared-memory
+ * bins, one 64-bit global atomic per bin per CTA).
+ * Replaces: frequency_measure.py:53-57 applied to saved labels; the quantity that
+ * freq_expert_select.py:61-64 averages and that is all-reduced across GPUs.
+ */
+MOE_API int moe_hist_accumulate(const int16_t* idx, long long n, int E, unsigned long long* hist, void* stream);
+
+/* Column max over tokens of a [T, C] f32 / bf16 matrix, max-accumulated into out[C]
+ * (expert_activation.py:57 on scores; predictivity.py:49 on act(gate)). */
+MOE_API int moe_colmax_f32(const float* m, int T, int C, float* out, void* stream);
+MOE_API int moe_colmax_bf16(const void* m, int T, int C, float* out, void* stream);
+
+/*
+ * Removal-mask utilities (remove_wanda_neurons_fast.py:13-29,72-77; multi_concept_remover.py:43-53).
+ *   moe_mask_pack:    dense u8 0/1 [n] -> bits u32 [ceil(n/32)]        (n % 32 tail handled)
+ *   moe_mask_union:   out = a | b over n_words words (out may alias a or b)
+ *   moe_mask_weights: W2m[r, c] = bit(r*h + c) ? 0 : W2[r, c]  for a [d, h] bf16 matrix
+ *                     (bits index the row-major flattening; requires h % 32 == 0)
+ */
+MOE_API int moe_mask_pack(const uint8_t* dense, long long n, uint32_t* bits, void* stream);
+MOE_API int moe_mask_union(const uint32_t* a, const uint32_t* b, uint32_t* out, long long n_words, void* stream);
+MOE_API int moe_mask_weights(const void* w2, const uint32_t* bits, void* w2m, int d, int h, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOE_B200_H */
