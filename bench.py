@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py -- the MoEfied GEGLU-FFN hot path of SD-1.5 on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--experts reference|literal]
+
+One *step* = one denoising step of the hot path: the 16 transformer-block FFNs of the SD-1.5 UNet
+(BASELINE.json configs[1]: batch 2 = CFG, 64x64 latents, bf16), each as K1 geglu_up -> K2 router
+(+ fused row-0 expert histogram + masking) -> K3 down_proj, through the C ABI of libmoe_b200.so, on
+synthetic hidden states and random-init weights of the SD-1.5 geometry.
+
+  value     tokens/s = token-FFN evaluations per second, whole job (N GPUs x 2 x 26 944 per step);
+            inputs resident in HBM, the step replayed as one CUDA graph; time = CUDA events, max over ranks.
+  e2e       same metric with HOST buffers: per step the 16 layer inputs are copied from pinned host memory,
+            the FFNs run through the C-ABI triple, outputs + histogram are copied back (all inside the timing).
+  roofline  dominant kernel (K1 geglu_up): algorithmic FLOPs (4 d h per token) / per-launch CUDA-event time.
+  cpu_baseline  the oracle port of the reference's hook arithmetic (fp32 torch-CPU, all host threads), timed
+            here on rank 0 at N=1 on a bounded sample (one layer per distinct shape x multiplicity).
+  --impl reference  times that CPU arm alone for K steps (the reference is pure Python on ATen and cannot be
+            installed without diffusers; the oracle port is bit-identical to it on CPU, see oracle/).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "diffusion-models-moe_b200"))
+
+import torch  # noqa: E402
+
+RATIO = 0.3
+# (d, tokens per sample at 64x64 latents, number of FFN layers of that shape), firing order groups
+SD15_LAYERS = [(320, 4096, 2), (640, 1024, 2), (1280, 256, 2), (1280, 64, 1), (1280, 256, 3), (640, 1024, 3),
+               (320, 4096, 3)]
+
+
+def layer_list():
+    out = []
+    for d, s, n in SD15_LAYERS:
+        out += [(d, 4 * d, s)] * n
+    return out
+
+
+def expert_size_for(mode, h):
+    return 20 if mode == "reference" else h // 20   # reference: 20 neurons/expert; literal: 20 experts
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--experts", default="reference", choices=["reference", "literal"])
+    ap.add_argument("--batch", type=int, default=2, help="UNet batch (2 = one prompt with CFG)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------- CPU arm
+def cpu_arm(args, steps, warmup):
+    """The reference's hook arithmetic (oracle port) on the host cores.  One step = the 16-layer sweep,
+    evaluated as one layer per distinct shape x its multiplicity (identical shapes cost the same)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import moe_ffn_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    shapes = {}
+    for d, h, s in layer_list():
+        shapes[(d, h, s)] = shapes.get((d, h, s), 0) + 1
+    layers = []
+    for (d, h, s), mult in shapes.items():
+        es = expert_size_for(args.experts, h)
+        layer = O.synthetic_layer(d, h, (args.batch, s), es, seed=d + s)
+        pat = O.patterns_from_labels(layer["labels"])
+        layers.append((layer, pat, O.topk_from_ratio(pat.shape[0], RATIO), mult))
+    tokens_per_step = args.batch * sum(s for _, _, s in layer_list())
+
+    def step():
+        total = 0.0
+        for layer, pat, k, mult in layers:
+            t0 = time.perf_counter()
+            with torch.no_grad():
+                H, labels, _, _ = O.moefy_forward(layer["x"], layer["w1"], layer["b1"], pat, k)
+                O.down_proj(H, layer["w2"], layer["b2"])
+                O.selection_counts(labels, pat.shape[0])
+            total += (time.perf_counter() - t0) * mult
+        return total
+
+    for _ in range(warmup):
+        step()
+    times = [step() for _ in range(steps)]
+    sec = statistics.median(times)
+    return dict(value=tokens_per_step / sec, unit="tokens/s", cores=cores, kind="port",
+                sample=f"{steps} x (one layer per distinct shape x multiplicity = 16-layer sweep, batch {args.batch}); "
+                       "oracle.moefy_forward + down_proj + counts, fp32 torch-CPU; median",
+                ms_per_step=sec * 1e3), tokens_per_step
+
+
+# --------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    QUERY = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.samples:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+# --------------------------------------------------------------------------------------- GPU arm
+def gpu_arm(args):
+    import moe_b200 as M
+    from moe_b200.packing import ExpertLayout, pack_ffn
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    M._lib.load()
+
+    B = args.batch
+    layers = []
+    gen = torch.Generator().manual_seed(1234 + rank)      # each rank = a different prompt shard
+    wgen = torch.Generator().manual_seed(0)               # weights are replicated
+    e_max = 0
+    for li, (d, h, s) in enumerate(layer_list()):
+        es = expert_size_for(args.experts, h)
+        E = h // es
+        e_max = max(e_max, E)
+        w1 = ((torch.rand(2 * h, d, generator=wgen) * 2 - 1) / d ** 0.5)
+        b1 = ((torch.rand(2 * h, generator=wgen) * 2 - 1) / d ** 0.5)
+        w2 = ((torch.rand(d, h, generator=wgen) * 2 - 1) / h ** 0.5)
+        b2 = ((torch.rand(d, generator=wgen) * 2 - 1) / h ** 0.5)
+        p = pack_ffn(ExpertLayout.contiguous(E, es), w1, b1, w2, b2, device=dev)
+        x_host = torch.nn.functional.layer_norm(torch.randn(B * s, d, generator=gen), (d,)).to(torch.bfloat16).pin_memory()
+        T = B * s
+        layers.append(dict(d=d, h=h, s=s, T=T, E=E, es=es, k=int(E * RATIO), p=p, x_host=x_host,
+                           x=x_host.to(dev), H=torch.empty(T, h, dtype=torch.bfloat16, device=dev),
+                           scores=torch.empty(T, E, dtype=torch.float32, device=dev),
+                           y=torch.empty(T, d, dtype=torch.bfloat16, device=dev),
+                           y_host=torch.empty(T, d, dtype=torch.bfloat16).pin_memory()))
+    hist = torch.zeros(len(layers), e_max, dtype=torch.int64, device=dev)
+    hist_host = torch.zeros(len(layers), e_max, dtype=torch.int64).pin_memory()
+    tokens_per_step = sum(L["T"] for L in layers)
+
+    def ffn_step(record=None):
+        for li, L in enumerate(layers):
+            p = L["p"]
+            if record is not None:
+                record(li, 0)
+            M.geglu_up(L["x"], p.w1p, p.b1p, L["E"], L["es"], M.ACT_GELU, out=L["H"], scores_out=L["scores"])
+            if record is not None:
+                record(li, 1)
+            M.router_topk(L["scores"], L["k"], want_bits=False, hist=hist[li, :L["E"]], H=L["H"], expert_size=L["es"],
+                          count_rows=(0, L["s"]))
+            if record is not None:
+                record(li, 2)
+            M.down_proj(L["H"], p.w2p, p.b2, out=L["y"])
+            if record is not None:
+                record(li, 3)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (also sets kernel attributes before any capture)
+    for _ in range(max(3, args.warmup)):
+        ffn_step()
+    torch.cuda.synchronize()
+    launches_per_step = 3 * len(layers)
+
+    graph = None
+    if not args.no_graph:
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            ffn_step()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(graph, stream=side):
+                ffn_step()
+        torch.cuda.current_stream().wait_stream(side)
+        for _ in range(3):
+            graph.replay()
+        torch.cuda.synchronize()
+
+    def run_step():
+        if graph is not None:
+            graph.replay()
+        else:
+            ffn_step()
+
+    # ---- timed region: K steps, device-resident inputs (working set ~0.5 GB >> 126 MB L2)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    hist.zero_()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        run_step()
+    if world > 1:
+        dist.all_reduce(hist, op=dist.ReduceOp.SUM)       # the path's only exchange: integer histograms
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    counts_ok = bool((hist[:, :].sum(1).cpu() == torch.tensor(
+        [world * args.steps * L["s"] * L["k"] for L in layers])).all())
+
+    # ---- instrumented pass: per-launch CUDA events (same inputs, K steps) for the kernel breakdown
+    per_kernel = [0.0, 0.0, 0.0]
+    k1_flops = sum(4.0 * L["d"] * L["h"] * L["T"] for L in layers)
+    k3_flops = sum(2.0 * L["d"] * L["h"] * L["T"] for L in layers)
+    n_inst = min(args.steps, 20)
+    for _ in range(n_inst):
+        evs = {}
+
+        def record(li, slot):
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            evs[(li, slot)] = e
+        ffn_step(record)
+        torch.cuda.synchronize()
+        for li in range(len(layers)):
+            for kk in range(3):
+                per_kernel[kk] += evs[(li, kk)].elapsed_time(evs[(li, kk + 1)])
+    per_kernel = [t / n_inst for t in per_kernel]           # ms per step spent in K1 / K2 / K3
+
+    # ---- e2e: host buffers through the C-ABI triple, H2D + D2H inside the timed region
+    h2d = sum(L["x_host"].numel() * 2 for L in layers)
+    d2h = sum(L["y_host"].numel() * 2 for L in layers) + hist_host.numel() * 8
+
+    def e2e_step():
+        for L in layers:
+            L["x"].copy_(L["x_host"], non_blocking=True)
+        ffn_step()
+        for L in layers:
+            L["y_host"].copy_(L["y"], non_blocking=True)
+        hist_host.copy_(hist, non_blocking=True)
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    n_e2e = min(args.steps, 20)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n_e2e):
+        e2e_step()
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1) / n_e2e
+
+    stats = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e = float(stats[0]), float(stats[1])
+    ms_step = ms_total / args.steps
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    peak_src = "fallback (B200_PROFILING.md)"
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        peak_src = "measured (MEASURED_PEAKS.json)"
+    except (OSError, ValueError):
+        peaks = {"bf16_tflops_sustained": 1400.0, "bf16_tflops": 1590.0, "hbm_gbs": 6650.0}
+    peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))   # kernel timed inside a long step
+    k1_tf = k1_flops / (per_kernel[0] * 1e-3) / 1e12
+    k3_tf = k3_flops / (per_kernel[2] * 1e-3) / 1e12
+    roofline = dict(bound="tensor", kernel="geglu_up_kernel (K1)", achieved=round(k1_tf, 2), peak=peak_tf,
+                    unit="TFLOP/s", frac=round(k1_tf / peak_tf, 4), traffic=None, peak_source=peak_src,
+                    algorithmic="4*d*h FLOP per token, summed over the 16 launches of a step / summed launch time",
+                    kernel_ms_per_step=dict(K1_geglu_up=round(per_kernel[0], 4), K2_router=round(per_kernel[1], 4),
+                                            K3_down_proj=round(per_kernel[2], 4)),
+                    K3_down_proj_tflops=round(k3_tf, 2), K3_frac=round(k3_tf / peak_tf, 4))
+
+    line = dict(metric="moe_ffn_tokens_per_s", value=world * tokens_per_step / (ms_step * 1e-3), unit="tokens/s",
+                n_gpus=world, steps=args.steps, warmup=max(3, args.warmup), ms_per_step=ms_step, higher_is_better=True,
+                scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
+                config=dict(workload="SD-1.5 MoEfied UNet, all 16 transformer-block FFNs, one denoising step, "
+                                     f"batch {B} (CFG), 64x64 latents (BASELINE configs[1])",
+                            experts=f"{args.experts}: expert_size {expert_size_for(args.experts, 1280)} @h=1280, "
+                                    f"top-k ratio {RATIO}",
+                            tokens_per_step_per_gpu=tokens_per_step, parallelism=f"prompt-sharded x{world}",
+                            l2="working set ~0.5 GB per step > 126 MB L2; no explicit flush",
+                            cuda_graph=graph is not None, counters="row-0 expert histogram fused in K2"),
+                unet_steps_per_s=world * 1e3 / ms_step,
+                e2e=dict(value=world * tokens_per_step / (ms_e2e * 1e-3), unit="tokens/s", h2d_bytes_per_step=h2d,
+                         d2h_bytes_per_step=d2h, ms_per_step=ms_e2e),
+                gpu_launches=launches_per_step * args.steps, clocks=clocks, roofline=roofline,
+                histogram_counts_exact=counts_ok)
+    if world == 1 and not args.no_cpu_baseline:
+        cb, _ = cpu_arm(args, steps=2, warmup=1)
+        line["cpu_baseline"] = cb
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return
+        cb, tokens = cpu_arm(args, steps=args.steps, warmup=args.warmup)
+        ms = cb.pop("ms_per_step")
+        line = dict(impl="reference", metric="moe_ffn_tokens_per_s", value=cb["value"], unit="tokens/s",
+                    n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=ms, higher_is_better=True,
+                    scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                    config=dict(workload="SD-1.5 MoEfied UNet, all 16 transformer-block FFNs, one denoising step, "
+                                         f"batch {args.batch} (CFG), 64x64 latents (BASELINE configs[1])",
+                                experts=args.experts, note="reference's hook arithmetic on the host CPU (oracle port; "
+                                "the Python reference needs diffusers, absent from this image)"),
+                    cpu_baseline=dict(cb, value=cb["value"]),
+                    e2e=dict(value=cb["value"], unit="tokens/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                    gpu_launches=0)
+        print(json.dumps(line))
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -71,11 +71,18 @@ def pack_ffn(layout: ExpertLayout, w1: torch.Tensor, b1: Optional[torch.Tensor],
     h = layout.hidden
     assert w1.shape[0] == 2 * h, (w1.shape, h)
     dev = device if device is not None else w1.device
-    perm = layout.perm.to(w1.device)
-    rows = torch.cat([perm, perm + h])
-    w1p = w1.detach()[rows].to(device=dev, dtype=torch.bfloat16).contiguous()
-    b1p = None if b1 is None else b1.detach()[rows].to(device=dev, dtype=torch.float32).contiguous()
-    w2p = None if w2 is None else w2.detach()[:, perm.to(w2.device)].to(device=dev, dtype=torch.bfloat16).contiguous()
+    if torch.equal(layout.perm, torch.arange(h)):
+        # already in packed order: alias bf16 parameters instead of copying them
+        w1s, b1s, w2s = w1.detach(), (None if b1 is None else b1.detach()), (None if w2 is None else w2.detach())
+    else:
+        perm = layout.perm.to(w1.device)
+        rows = torch.cat([perm, perm + h])
+        w1s = w1.detach()[rows]
+        b1s = None if b1 is None else b1.detach()[rows]
+        w2s = None if w2 is None else w2.detach()[:, perm.to(w2.device)]
+    w1p = w1s.to(device=dev, dtype=torch.bfloat16).contiguous()
+    b1p = None if b1s is None else b1s.to(device=dev, dtype=torch.float32).contiguous()
+    w2p = None if w2s is None else w2s.to(device=dev, dtype=torch.bfloat16).contiguous()
     b2f = None if b2 is None else b2.detach().to(device=dev, dtype=torch.float32).contiguous()
     return PackedFFN(layout, w1p, b1p, w2p, b2f)
 

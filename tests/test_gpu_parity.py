@@ -1,0 +1,280 @@
+"""GPU parity tests proper: every kernel, through the C ABI, against the oracle on the same
+seeded inputs; against the committed golden vectors from the reference; and, at BASELINE.json's
+full sizes, through size-independent properties."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import moe_b200 as M
+import moe_ffn_oracle as O
+from moe_b200.packing import ExpertLayout, pack_ffn, bits_to_sets
+from gpu_util import DEV, cuda_layer, oracle_layer, check_layer, rel_err, r16, label_sets, OUT_REL_TOL
+
+pytestmark = pytest.mark.gpu
+
+
+def load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name + ".npz"), allow_pickle=False)
+
+
+def T(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+# ------------------------------------------------------------------------------------ whole layer
+LAYER_CASES = [
+    # d, h, (B, S), es, ratio, act
+    (32, 128, (2, 48), 16, 0.3, O.ACT_GELU),
+    (64, 320, (2, 40), 20, 0.3, O.ACT_GELU),
+    (64, 320, (1, 1), 20, 0.5, O.ACT_RELU),        # single token
+    (32, 128, (3, 43), 16, 1.0, O.ACT_GELU),       # k == E, ragged token count
+    (40, 160, (1, 130), 8, 0.25, O.ACT_GELU),      # d not a multiple of 64 (TMA zero-fills the K tail)
+    (320, 1280, (1, 1024), 20, 0.3, O.ACT_GELU),   # SD-1.5 down_blocks.0 geometry, reference experts
+    (320, 1280, (1, 1024), 64, 0.3, O.ACT_RELU),   # BASELINE-literal 20 experts of 64
+    (640, 2560, (2, 256), 20, 0.3, O.ACT_GELU),
+    (1280, 5120, (2, 64), 20, 0.3, O.ACT_GELU),    # mid-block geometry, E = 256
+]
+
+
+@pytest.mark.parametrize("d,h,shape,es,ratio,act", LAYER_CASES)
+def test_layer_matches_oracle(lib, d, h, shape, es, ratio, act):
+    layer = O.synthetic_layer(d, h, shape, es, seed=d + es)
+    cu = cuda_layer(layer, ratio, act)
+    orc = oracle_layer(layer, ratio, act)
+    stats = check_layer(cu, orc, min_safe_fraction=0.85)
+    # fused histogram == bincount of the kernel's own labels (batch row 0 only, reference policy)
+    S = shape[1]
+    assert torch.equal(cu["hist"], torch.bincount(cu["idx"][:S].reshape(-1), minlength=cu["E"]))
+    assert int(cu["hist"].sum()) == S * cu["k"]
+    assert torch.allclose(cu["colmax"], cu["scores"].max(0)[0])
+    print(stats)
+
+
+@pytest.mark.parametrize("name", ["moefy_small_gelu", "moefy_small_relu", "moefy_es20", "moefy_k_equals_E",
+                                  "moefy_ragged"])
+def test_layer_matches_reference_golden(lib, golden_dir, name):
+    """Against the reference's own fp32 output (golden fixture): bf16 kernels vs fp32 reference."""
+    g = load(golden_dir, name)
+    layer = dict(x=T(g["x"]), w1=T(g["w1"]), b1=T(g["b1"]), w2=T(g["w2"]), b2=T(g["b2"]), labels=g["labels"])
+    cu = cuda_layer(layer, float(g["ratio"]), int(g["act"]), count_rows=(0, int(g["shape"][1])))
+    E = int(g["E"])
+    ref_sets = bits_to_sets(T(g["bitmask"].view(np.int32)), E)
+    margin = g["margin"]
+    wide = margin > 0.25          # bf16 input rounding moves scores by ~1e-2; only wide margins are pinned
+    agree = np.array([cu["sets"][t] == ref_sets[t] for t in range(len(ref_sets))])
+    assert agree[wide].all()
+    n = len(ref_sets)
+    Hc, Hr = cu["H"].reshape(n, -1), T(g["H"]).reshape(n, -1)
+    yc, yr = cu["y"].reshape(n, -1), T(g["y"]).reshape(n, -1)
+    assert rel_err(Hc[agree], Hr[agree]) < OUT_REL_TOL
+    assert rel_err(yc[agree], yr[agree]) < OUT_REL_TOL
+    assert torch.allclose(cu["scores"], T(g["score"]), atol=0.1)
+    # the reference's sign assertion (moefy.py:50-51): gates non-negative iff ReLU
+    gate = cuda_layer(layer, float(g["ratio"]), int(g["act"]), want_gate=True)["gate"]
+    assert bool(torch.all(gate >= 0)) == (int(g["act"]) == O.ACT_RELU)
+
+
+# ------------------------------------------------------------------------------------ router alone
+@pytest.mark.parametrize("Tn,E,k", [(1, 8, 2), (33, 20, 6), (257, 64, 19), (100, 64, 64), (64, 128, 38),
+                                     (300, 256, 76), (50, 256, 230), (17, 96, 1), (5, 40, 0)])
+def test_router_bit_exact_on_given_scores(lib, Tn, E, k):
+    g = torch.Generator().manual_seed(E * 1000 + k)
+    scores = torch.randn(Tn, E, generator=g)
+    scores[::3] = scores[::3].abs() * 5        # rows whose keys share sign/exponent prefixes
+    scores[1::5] *= 1e-3
+    dsc = scores.to(DEV)
+    hist = torch.zeros(E, dtype=torch.int64, device=DEV)
+    cmax = torch.full((E,), float("-inf"), device=DEV)
+    bits, idx = M.router_topk(dsc, k, want_idx=True, hist=hist, colmax_out=cmax, count_rows=(0, Tn))
+    torch.cuda.synchronize()
+    want = torch.topk(scores, k, dim=-1)[1].sort(dim=-1)[0] if k > 0 else torch.zeros(Tn, 0, dtype=torch.long)
+    assert torch.equal(idx.cpu().long(), want)                               # ascending expert ids
+    assert bits_to_sets(bits, E) == [set(r.tolist()) for r in want]
+    assert torch.equal(hist.cpu(), torch.bincount(want.reshape(-1), minlength=E))
+    assert torch.equal(cmax.cpu(), scores.max(0)[0])
+
+
+def test_router_ties_and_removed_experts(lib):
+    """Removed experts score exactly 0, still compete for slots, own no neurons
+    (remove_skilled_experts.py:29-49); exact ties go to the lower expert id."""
+    E, es, k = 16, 4, 6
+    scores = torch.full((4, E), -1.0)
+    scores[0, [3, 9]] = 2.0          # 2 positive, rest -1: removed experts (score 0) fill the slots
+    scores[1] = torch.arange(E).float()
+    scores[2] = 1.0                  # all tied
+    scores[3, :] = torch.tensor([5., 4, 3, 2, 1, 0.5] + [-2.] * 10)
+    removed = [1, 2, 12, 13, 14]
+    H = torch.ones(4, E * es, dtype=torch.bfloat16, device=DEV)
+    bits, idx = M.router_topk(scores.to(DEV), k, removed_bits=M.bits_from_expert_list(removed, E).to(DEV), want_idx=True,
+                              H=H, expert_size=es)
+    torch.cuda.synchronize()
+    idx = idx.cpu().long()
+    assert idx[0].tolist() == [1, 2, 3, 9, 12, 13]       # 3, 9 then zeros (removed) by lowest id; -1s lose
+    assert idx[1].tolist() == [7, 8, 9, 10, 11, 15]
+    s1 = scores[1].clone(); s1[removed] = 0
+    assert set(idx[1].tolist()) == set(torch.topk(s1, k)[1].tolist())
+    assert idx[2].tolist() == [0, 3, 4, 5, 6, 7]          # removed experts have score 0 < 1; ties -> lowest ids
+    assert idx[3].tolist() == [0, 1, 2, 3, 4, 5]         # 5, 2, 1, 0.5 then two zero-score removed experts
+    active = bits_to_sets(bits, E)
+    for t in range(4):
+        assert active[t] == set(idx[t].tolist()) - set(removed)
+        keep = torch.zeros(E); keep[list(active[t])] = 1
+        assert torch.equal(H[t].float().cpu(), keep.repeat_interleave(es))
+
+
+def test_router_matches_remove_experts_golden(lib, golden_dir):
+    for name in ["remove_experts_small", "remove_experts_crowded"]:
+        g = load(golden_dir, name)
+        layer = dict(x=T(g["x"]), w1=T(g["w1"]), b1=T(g["b1"]), w2=torch.zeros(32, 128), b2=torch.zeros(32),
+                     labels=g["labels"])
+        removed = [int(v) for v in g["removed"]]
+        for (t, l) in [(0, 0), (0, 1), (19, 0), (20, 0)]:
+            lst = removed if (l == 0 and t < 20) else []
+            cu = cuda_layer(layer, float(g["ratio"]), removed=lst)
+            orc = oracle_layer(layer, float(g["ratio"]), removed=lst, timestep=t)
+            want = label_sets(orc["labels"])
+            safe = (orc["margin"] > 2e-3).numpy()
+            n = len(want)
+            # selected sets (incl. removed experts that took a slot) == reference labels
+            got = [set(r.tolist()) for r in cu["idx"]]
+            agree = np.array([got[i] == want[i] for i in range(n)])
+            if cu["k"] < cu["E"]:
+                assert agree[safe].all()
+            else:
+                assert agree.all()
+            Hc, Hr = cu["H"].reshape(n, -1), T(g[f"H_t{t}_l{l}"]).reshape(n, -1)
+            assert rel_err(Hc[agree], Hr[agree]) < OUT_REL_TOL
+            if lst:   # removed experts' neurons are always masked
+                pat = O.patterns_from_labels(g["labels"])
+                dead = pat[lst].sum(0) > 0
+                assert torch.all(Hc[:, dead] == 0)
+
+
+# ------------------------------------------------------------------------------------ other kernels
+def test_remove_neurons_override_matches_golden(lib, golden_dir):
+    g = load(golden_dir, "remove_neurons_small")
+    layer = dict(x=T(g["x"]), w1=T(g["w1"]), b1=T(g["b1"]), w2=torch.zeros(32, 128), b2=torch.zeros(32),
+                 labels=O.balanced_labels(128, 16, 0))
+    cu = cuda_layer(layer, 1.0, flags=g["flags"].tolist(), want_gate=True)
+    assert rel_err(cu["H_unmasked"], T(g["H_removed"])) < OUT_REL_TOL
+    idx = np.nonzero(g["flags"])[0]
+    assert torch.all(cu["gate"][..., idx] == torch.tensor(-0.17).bfloat16().float())
+    plain = cuda_layer(layer, 1.0)
+    assert rel_err(plain["H_unmasked"], T(g["H_plain"])) < OUT_REL_TOL
+
+
+def test_expert_predictivity_matches_golden(lib, golden_dir):
+    g = load(golden_dir, "expert_predictivity_small")
+    lay = ExpertLayout.from_labels(g["labels"])
+    p = pack_ffn(lay, T(g["w1"]), T(g["b1"]), device=DEV)
+    for x, want in zip(g["xs"], g["max_gate"]):
+        xt = T(x).reshape(-1, x.shape[-1]).to(DEV, torch.bfloat16)
+        H, scores, _ = M.geglu_up(xt, p.w1p, p.b1p, lay.n_experts, lay.expert_size)
+        got = M.colmax(scores).cpu().numpy()
+        assert np.allclose(got, want, atol=0.05)
+        assert np.array_equal(got, scores.max(0)[0].cpu().numpy())
+
+
+@pytest.mark.parametrize("Tn,h,d", [(1, 64, 16), (100, 128, 48), (256, 1280, 320), (2048, 2560, 640), (512, 5120, 1280)])
+def test_down_proj_matches_fp32(lib, Tn, h, d):
+    g = torch.Generator().manual_seed(h + d)
+    H = (torch.randn(Tn, h, generator=g) * 0.5)
+    W = torch.randn(d, h, generator=g) / h ** 0.5
+    b = torch.randn(d, generator=g)
+    y = M.down_proj(H.to(DEV, torch.bfloat16), W.to(DEV, torch.bfloat16), b.to(DEV)).float().cpu()
+    ref = O.down_proj(r16(H), r16(W), b)
+    assert rel_err(y, ref) < 4e-3          # bf16 output rounding only
+    assert torch.allclose(y, ref, rtol=1e-2, atol=2e-2)
+
+
+def test_histogram_kernel(lib):
+    for n, E in [(1, 8), (7, 20), (4096 * 19, 64), (100003, 256)]:
+        idx = torch.randint(0, E, (n,), generator=torch.Generator().manual_seed(n), dtype=torch.int16)
+        hist = M.hist_accumulate(idx.to(DEV), E)
+        assert torch.equal(hist.cpu(), torch.bincount(idx.long(), minlength=E))
+        M.hist_accumulate(idx.to(DEV), E, hist)                     # accumulates
+        assert torch.equal(hist.cpu(), 2 * torch.bincount(idx.long(), minlength=E))
+    # unaligned view (scalar path) and empty input
+    idx = torch.randint(0, 64, (1001,), dtype=torch.int16).to(DEV)
+    assert torch.equal(M.hist_accumulate(idx[1:], 64).cpu(), torch.bincount(idx[1:].cpu().long(), minlength=64))
+    assert int(M.hist_accumulate(idx[:0], 64).sum()) == 0
+
+
+def test_mask_kernels_on_reference_fixture(lib, golden_dir):
+    """Bit-packing / union / weight masking, bit-exact on the reference's real Wanda masks."""
+    g = load(golden_dir, "wanda_csv_320_1280")
+    masks = np.unpackbits(g["packed"], axis=2, bitorder="little")            # [5, 320, 1280] 0/1
+    packed = [M.mask_pack(T(m).to(DEV)) for m in masks]
+    for bits, want in zip(packed, g["packed"]):
+        assert np.array_equal(bits.cpu().numpy().view(np.uint8), want.reshape(-1))
+    u = packed[0].clone()
+    for b in packed[1:]:
+        M.mask_union(u, b, out=u)
+    assert np.array_equal(u.cpu().numpy().view(np.uint8), g["union_packed"].reshape(-1))
+    W = torch.randn(320, 1280, generator=torch.Generator().manual_seed(0)).to(DEV, torch.bfloat16)
+    Wm = M.mask_weights(W, u)
+    union = np.unpackbits(g["union_packed"], axis=1, bitorder="little").astype(bool)
+    assert torch.equal(Wm.cpu(), torch.where(T(union), torch.zeros((), dtype=torch.bfloat16), W.cpu()))
+    # ragged tail of mask_pack
+    d = torch.randint(0, 2, (77,), dtype=torch.uint8)
+    assert np.array_equal(M.mask_pack(d.to(DEV)).cpu().numpy().view(np.uint8)[:10],
+                          np.packbits(d.numpy(), bitorder="little"))
+
+
+def test_wanda_down_proj_matches_golden(lib, golden_dir):
+    g = load(golden_dir, "wanda_small")
+    hid = T(g["hid"]).reshape(-1, 128).to(DEV, torch.bfloat16)
+    W, b = T(g["w2"]).to(DEV, torch.bfloat16), T(g["b2"]).to(DEV)
+    for mask, want in [(g["mask_a"], g["y_a"]), (g["union"], g["y_union"]), (np.zeros_like(g["union"]), g["y_stock"])]:
+        Wm = M.mask_weights(W, M.mask_pack(T(mask).to(DEV)))
+        y = M.down_proj(hid, Wm, b).float().cpu().view(*want.shape)
+        assert rel_err(y, T(want)) < OUT_REL_TOL
+    ua = M.mask_union(M.mask_union(M.mask_pack(T(g["mask_a"]).to(DEV)), M.mask_pack(T(g["mask_b"]).to(DEV))),
+                      M.mask_pack(T(g["mask_c"]).to(DEV)))
+    assert torch.equal(ua, M.mask_pack(T(g["union"]).to(DEV)))
+
+
+# ------------------------------------------------------------------------------------ full sizes
+@pytest.mark.parametrize("d,h,B,S,es,ratio", [(320, 1280, 2, 4096, 20, 0.3), (320, 1280, 16, 4096, 64, 0.3),
+                                               (1280, 5120, 16, 256, 20, 0.3), (320, 1280, 2, 9216, 20, 0.5)])
+def test_full_size_properties(lib, d, h, B, S, es, ratio):
+    """BASELINE.json sizes (configs 2/3/5): properties that need no oracle run."""
+    E = h // es
+    k = int(E * ratio)
+    gen = torch.Generator().manual_seed(S + es)
+    x = torch.randn(B * S, d, generator=gen).to(DEV, torch.bfloat16)
+    w1 = (torch.randn(2 * h, d, generator=gen) / d ** 0.5).to(DEV, torch.bfloat16)
+    b1 = (torch.randn(2 * h, generator=gen) * 0.1).to(DEV)
+    w2 = (torch.randn(d, h, generator=gen) / h ** 0.5).to(DEV, torch.bfloat16)
+    H, scores, _ = M.geglu_up(x, w1, b1, E, es)
+    H0 = H.clone()
+    hist_row0 = torch.zeros(E, dtype=torch.int64, device=DEV)
+    hist_all = torch.zeros(E, dtype=torch.int64, device=DEV)
+    bits, idx = M.router_topk(scores, k, want_idx=True, hist=hist_row0, H=H, expert_size=es, count_rows=(0, S))
+    bits2, _ = M.router_topk(scores, k, hist=hist_all, count_rows=(0, B * S))
+    assert torch.equal(bits, bits2)                                           # deterministic
+    assert int(hist_row0.sum()) == S * k and int(hist_all.sum()) == B * S * k
+    assert torch.equal(hist_all, M.hist_accumulate(idx, E))                   # fused == standalone histogram
+    assert torch.equal(hist_all.cpu(), torch.bincount(idx.reshape(-1).long().cpu(), minlength=E))
+    # every token keeps exactly k experts' neurons, untouched; the rest is exactly zero
+    keep = torch.zeros(B * S, E, device=DEV).scatter_(1, idx.long(), 1.0).bool().repeat_interleave(es, dim=1)
+    assert torch.equal(H, torch.where(keep, H0, torch.zeros((), dtype=torch.bfloat16, device=DEV)))
+    # selected scores dominate unselected ones
+    sel = torch.zeros(B * S, E, device=DEV, dtype=torch.bool).scatter_(1, idx.long(), True)
+    lo = torch.where(sel, scores, torch.full_like(scores, float("inf"))).min(1)[0]
+    hi = torch.where(sel, torch.full_like(scores, float("-inf")), scores).max(1)[0]
+    assert bool((lo >= hi).all())
+    # idempotence: masking an already masked H changes nothing
+    H1 = H.clone()
+    M.router_topk(scores, k, want_bits=False, H=H1, expert_size=es)
+    assert torch.equal(H, H1)
+    # scores are the segment sums of the activated gate; the GEMMs match a torch fp32 matmul on a row sample
+    rows = torch.arange(0, B * S, max(1, (B * S) // 256), device=DEV)
+    yref = x[rows].float() @ w1.float().t() + b1
+    v, g = yref[:, :h], torch.nn.functional.gelu(yref[:, h:])
+    assert torch.allclose(scores[rows], g.view(len(rows), E, es).sum(-1), atol=5e-4, rtol=1e-5)
+    assert rel_err(H0[rows].float(), v * g) < 4e-3
+    y = M.down_proj(H, w2, None)
+    assert rel_err(y[rows].float(), H[rows].float() @ w2.float().t()) < 4e-3
