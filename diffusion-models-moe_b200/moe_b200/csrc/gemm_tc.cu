@@ -318,13 +318,22 @@ down_proj_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_consta
 #pragma unroll
         for (int i = 0; i < CH; i += 2) {
           float y0 = __uint_as_float(acc[i]), y1 = __uint_as_float(acc[i + 1]);
-          if (a.b2 != nullptr) {
-            y0 += __ldg(a.b2 + n + i);
-            y1 += __ldg(a.b2 + n + i + 1);
+          if (a.b2 != nullptr) {  // indices clamped: the last tile may overhang d
+            y0 += __ldg(a.b2 + min(n + i, a.d - 1));
+            y1 += __ldg(a.b2 + min(n + i + 1, a.d - 1));
           }
           yw[i / 2] = pack_bf16x2(y0, y1);
         }
-        if (row_ok) store_words<CH / 2>(a.Y + static_cast<size_t>(row) * a.d + n, yw);
+        if (row_ok) {
+          __nv_bfloat16* dst = a.Y + static_cast<size_t>(row) * a.d + n;
+          if (n + CH <= a.d) {
+            store_words<CH / 2>(dst, yw);
+          } else {  // last tile of a d that is not a multiple of the tile width
+#pragma unroll
+            for (int i = 0; i < CH / 2; ++i)
+              if (n + 2 * i < a.d) *reinterpret_cast<uint32_t*>(dst + 2 * i) = yw[i];
+          }
+        }
       }
       tc::fence_before_thread_sync();
       __syncwarp();
@@ -341,7 +350,7 @@ static int fill_shape(GemmShape& g, int rows, int k, int n_total, int tile_n, in
   g.rows = rows;
   g.k = k;
   g.m_tiles = (rows + kBlockM - 1) / kBlockM;
-  g.n_tiles = n_total / (tile_n == b_rows ? tile_n : b_rows);
+  g.n_tiles = (n_total + b_rows - 1) / b_rows;
   g.tile_n = tile_n;
   g.b_rows = b_rows;
   g.stage_bytes = kABytes + tile_n * 128;
@@ -442,18 +451,19 @@ int moe_geglu_up(const void* x, const void* w1p, const float* b1p, const uint8_t
 int moe_down_proj(const void* H, const void* w2p, const float* b2, void* Y, int T, int h, int d, void* stream) {
   using namespace moe;
   MOE_REQUIRE(H && w2p && Y, MOE_ERR_INVALID_ARGUMENT, "moe_down_proj: NULL H / w2p / Y");
-  MOE_REQUIRE(T >= 0 && h >= 8 && d >= 16, MOE_ERR_INVALID_ARGUMENT, "moe_down_proj: bad sizes T=%d h=%d d=%d", T, h, d);
-  MOE_REQUIRE(h % 8 == 0 && d % 16 == 0, MOE_ERR_UNSUPPORTED_SHAPE, "moe_down_proj: h=%d %% 8, d=%d %% 16 required", h, d);
+  MOE_REQUIRE(T >= 0 && h >= 8 && d >= 8, MOE_ERR_INVALID_ARGUMENT, "moe_down_proj: bad sizes T=%d h=%d d=%d", T, h, d);
+  MOE_REQUIRE(h % 8 == 0 && d % 8 == 0, MOE_ERR_UNSUPPORTED_SHAPE, "moe_down_proj: h=%d and d=%d must be multiples of 8", h, d);
   MOE_REQUIRE((reinterpret_cast<uintptr_t>(Y) & 15) == 0, MOE_ERR_INVALID_ARGUMENT, "moe_down_proj: Y must be 16-byte aligned");
   if (T == 0) return MOE_OK;
-  // tile width: a multiple of 16 dividing d, <= 256; pick the one with the best wave-quantised cost
+  // tile width: a multiple of 16, <= 256 (the last tile may overhang d: TMA zero-fills the missing
+  // weight rows and the epilogue guards its stores); pick the best wave-quantised cost
   const int m_tiles = (T + kBlockM - 1) / kBlockM;
   const int sms = sm_count();
   int best = 0;
   double best_cost = 1e30;
   for (int bn = 256; bn >= 16; bn -= 16) {
-    if (d % bn) continue;
-    const long long tiles = static_cast<long long>(m_tiles) * (d / bn);
+    if (bn - (d % bn ? d % bn : bn) >= 16) continue;  // never waste a whole 16-column group
+    const long long tiles = static_cast<long long>(m_tiles) * ((d + bn - 1) / bn);
     const long long waves = (tiles + sms - 1) / sms;
     // per-tile MMA time ~ max(bn/2, smem-bound (4096 + 32 bn)/128) cycles per K step
     const double per_tile = bn / 2.0 > (4096.0 + 32.0 * bn) / 128.0 ? bn / 2.0 : (4096.0 + 32.0 * bn) / 128.0;
