@@ -29,6 +29,7 @@ SIGNATURES = {
     "moe_mask_pack": (c_int, [c_void_p, c_ll, c_void_p, c_void_p]),
     "moe_mask_union": (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_void_p]),
     "moe_mask_weights": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "moe_debug_counters": (c_int, [c_void_p, c_int]),
 }
 
 ABI_VERSION = 1

@@ -1,19 +1,31 @@
 // K1 (GEGLU up-projection, fused activation / override / expert-score epilogue) and
 // K3 (down-projection) for sm_100a: persistent, warp-specialised tcgen05 GEMMs.
 //
-//   warp 0     : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier tx-count)
-//   warp 1     : MMA issuer     (one thread issues tcgen05.mma, accumulators in TMEM, 2 stages)
-//   warp 2     : TMEM allocator
-//   warp 3     : idle
-//   warps 4-11 : epilogue       (tcgen05.ld -> registers -> fused math -> global), two column groups
-//                               x four TMEM lane quarters, overlapped with the next tile's MMAs
+//   warp 0      : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier tx-count;
+//                                 operand slices are MULTICAST across a thread-block cluster)
+//   warp 1      : MMA issuer     (one thread issues tcgen05.mma, accumulators in TMEM, 2 stages)
+//   warp 2      : TMEM allocator
+//   warp 3      : idle
+//   warps 4-19  : epilogue       (tcgen05.ld -> registers -> fused math -> smem/global), four column
+//                                 groups x four TMEM lane quarters, overlapped with the next tile's MMAs
 //
 // Operands are bf16, both K-major: A = activations [rows, K], B = weights [N, K] (nn.Linear layout),
 // so D[m, n] = sum_k A[m, k] B[n, k] needs no transposes.  One UMMA per 16-wide K step covers the
 // whole tile width; for K1 the B tile is [value rows | gate rows] so that value and gate
 // accumulators of the same neurons sit side by side in one TMEM stage.
+//
+// Clusters.  Every launch measured L2->SM bound with 128 x 160 tiles (panel traffic = 2 M N K
+// (1/BM + 1/BN) bytes), so CTAs are grouped in clusters of cn x cm: the cn CTAs of a cluster row work
+// on the same 128 token rows and each loads 1/cn of the A tile and multicasts it to the row; the cm
+// CTAs of a cluster column work on the same weight rows and each loads 1/cm of the B tile and
+// multicasts it to the column.  A smem slot may be overwritten only when every CTA that receives
+// the sender's slices has consumed it, so the MMA thread's tcgen05.commit multicasts its "slot free"
+// arrive to all of its senders and each empty barrier expects cn + cm - 1 arrivals.
 #include "common.cuh"
 #include "tcgen05.cuh"
+
+#include <stdlib.h>
+#include <utility>
 
 namespace moe {
 
@@ -23,11 +35,18 @@ constexpr int kUmmaK = 16;
 constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KiB
 constexpr int kAccStride = 256;                  // TMEM columns between the two accumulator stages
 constexpr int kTmemCols = 512;
-constexpr int kNumThreads = 384;
 constexpr int kEpiWarp0 = 4;
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 16;
+constexpr int kColGroups = kEpiWarps / 4;        // column groups per TMEM lane quarter
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kNumThreads = kEpiWarp0 * 32 + kEpiThreads;   // 640
 constexpr int kMaxStages = 8;
 constexpr int kSmemLimit = 232448;               // 227 KiB opt-in dynamic shared memory
+constexpr int kBiasSmemPerWarp = 128 * 4;        // 2 x 64 floats
+constexpr int kEpiBarrierId = 1;
+
+// profiling counters (MOE_DEBUG_MODE bit 16): per CTA, cycles the producer / MMA threads spend per step
+__device__ unsigned long long g_dbg_counters[256 * 8];
 
 struct PipeBarriers {
   uint64_t full[kMaxStages];
@@ -38,17 +57,40 @@ struct PipeBarriers {
 };
 
 struct GemmShape {
-  int rows;        // M (tokens)
-  int k;           // reduction length
-  int m_tiles;
-  int n_tiles;
-  int tile_n;      // UMMA N (accumulator columns per stage)
-  int b_rows;      // rows per B TMA box (tile_n for K3, tile_n/2 for K1: two boxes per stage)
-  int stages;
-  int stage_bytes;
+  int rows;          // M (tokens)
+  int k;             // reduction length
+  int m_tiles, n_tiles;
+  int tile_n;        // UMMA N (accumulator columns per stage) = B rows per stage
+  int half_rows;     // K1: nv (value rows, then gate rows); K3: tile_n
+  int second_off;    // K1: global row offset of the gate half (h); K3: 0
+  int stages, stage_bytes;
+  int cn, cm;        // cluster: cn CTAs share the A tile, cm CTAs share the B tile
+  int a_box_rows;    // 128 / cn
+  int b_box_rows;    // rows per B TMA box issued by one CTA
+  int b_boxes;       // B boxes one CTA issues per stage
+  int m_ctiles, n_ctiles;
+  int extra_smem;    // bytes after the stage ring (epilogue staging)
+  int pair;          // 1: cta_group::2 -- the two CTAs of a cluster pair share one 256 x tile_n UMMA
+  int debug;         // MOE_DEBUG_MODE bits: 1 = no TMA loads, 2 = no MMAs, 4 = no epilogue math (profiling only)
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// exact GELU x * Phi(x) with Phi from 0.5 * erfc(|x|/sqrt2) = 2^(P7(t)), t = min(|x|/sqrt2, 4.3):
+// branch-free, one MUFU.EX2 + 7 FFMA; max abs error 4e-7 on [-3, 3] (fp32 rounding level; the
+// libdevice erff path costs ~2x the instructions and diverges).  Coefficients: weighted minimax fit.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float t = fminf(fabsf(x) * 0.70710678118654752f, 4.3f);
+  float q = 1.0664232831913978e-04f;
+  q = fmaf(q, t, -5.025442806072533e-04f);
+  q = fmaf(q, t, -2.20537674613297e-03f);
+  q = fmaf(q, t, 2.9348013922572136e-02f);
+  q = fmaf(q, t, -1.4891357719898224e-01f);
+  q = fmaf(q, t, -9.183364510536194e-01f);
+  q = fmaf(q, t, -1.6279140710830688f);
+  q = fmaf(q, t, -0.9999999403953552f);
+  const float e = tc::ex2_approx(q);               // 0.5 * erfc(t)
+  const float phi = x >= 0.f ? 1.0f - e : e;
+  return x * phi;
+}
 
 template <int ACT>
 __device__ __forceinline__ float activate(float x) {
@@ -63,7 +105,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&p);
 }
 
-// store kN packed bf16 pairs (kN/2 words) to a row pointer with the widest aligned vectors
+// store kWords 32-bit words with the widest vectors the (known) alignment allows
 template <int kWords>
 __device__ __forceinline__ void store_words(__nv_bfloat16* dst, const uint32_t* w) {
   if constexpr (kWords % 4 == 0) {
@@ -77,73 +119,189 @@ __device__ __forceinline__ void store_words(__nv_bfloat16* dst, const uint32_t* 
 }
 
 // ------------------------------------------------------------------------------------------
+// Tile schedule: cluster c takes cluster tiles c, c + n_clusters, ...; inside a cluster tile the
+// CTA of rank (rn, rm) owns CTA tile (m = mct * cm + rm, n = nct * cn + rn).
+// ------------------------------------------------------------------------------------------
+struct TileCoord {
+  int m_blk, n_blk;
+};
+__device__ __forceinline__ bool tile_at(const GemmShape& g, int it, int rn, int rm, TileCoord& t) {
+  const int csize = g.cn * g.cm;
+  const int ct = static_cast<int>(blockIdx.x) / csize + it * (static_cast<int>(gridDim.x) / csize);
+  if (ct >= g.m_ctiles * g.n_ctiles) return false;
+  t.m_blk = (ct / g.n_ctiles) * g.cm + rm;
+  t.n_blk = (ct % g.n_ctiles) * g.cn + rn;
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------
 // Shared mainloop roles
 // ------------------------------------------------------------------------------------------
-template <bool kTwoBBoxes>
+// Two producer threads (warp 0: A tiles + barrier arming, warp 3: B tiles): one thread pays ~200
+// cycles per TMA instruction, which alone would pace the ring slower than the tensor pipe drains it.
+template <bool PAIR>
 __device__ __forceinline__ void producer_loop(const CUtensorMap* tmap_a, const CUtensorMap* tmap_b, uint8_t* smem,
-                                              PipeBarriers* bars, const GemmShape& g, int b_row_offset2) {
+                                              PipeBarriers* bars, const GemmShape& g, int rn, int rm, bool do_a) {
   const int num_kb = (g.k + kBlockK - 1) / kBlockK;
-  const int total = g.m_tiles * g.n_tiles;
+  uint16_t row_mask = 0, col_mask = 0;   // CTAs sharing my A tile / my B tile
+  for (int j = 0; j < g.cn; ++j) row_mask |= static_cast<uint16_t>(1u << (rm * g.cn + j));
+  for (int i = 0; i < g.cm; ++i) col_mask |= static_cast<uint16_t>(1u << (i * g.cn + rn));
+  const int b_slice_rows = g.tile_n / g.cm;
+  constexpr bool pair = PAIR;
   int s = 0;
   uint32_t ph = 0;
-  for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-    const int m_blk = tile / g.n_tiles, n_blk = tile % g.n_tiles;
+  TileCoord t;
+  const bool prof = (g.debug & 16) != 0 && do_a;
+  long long c_wait = 0, c_issue = 0, n_iter = 0;
+  for (int it = 0; tile_at(g, it, rn, rm, t); ++it) {
     for (int kb = 0; kb < num_kb; ++kb) {
+      const long long t0 = prof ? clock64() : 0;
       tc::mbar_wait(&bars->empty[s], ph ^ 1u);
+      const long long t1 = prof ? clock64() : 0;
+      c_wait += t1 - t0;
+      ++n_iter;
       uint8_t* sa = smem + s * g.stage_bytes;
       uint8_t* sb = sa + kABytes;
-      tc::mbar_arrive_expect_tx(&bars->full[s], static_cast<uint32_t>(g.stage_bytes));
-      tc::tma_load_2d(sa, tmap_a, &bars->full[s], kb * kBlockK, m_blk * kBlockM);
-      tc::tma_load_2d(sb, tmap_b, &bars->full[s], kb * kBlockK, n_blk * g.b_rows);
-      if constexpr (kTwoBBoxes)
-        tc::tma_load_2d(sb + g.b_rows * 128, tmap_b, &bars->full[s], kb * kBlockK, b_row_offset2 + n_blk * g.b_rows);
+      if (tc::elect_one()) {
+      if (g.debug & 1) {   // profiling: pretend the stage arrived
+        if (do_a && (!pair || rm == 0)) tc::mbar_arrive(&bars->full[s]);
+      } else if constexpr (pair) {
+        // the leader's barrier collects the bytes of both CTAs of the pair
+        const uint32_t full_leader = tc::mapa_u32(&bars->full[s], 0);
+        if (do_a) {
+          if (rm == 0) tc::mbar_arrive_expect_tx(&bars->full[s], static_cast<uint32_t>(2 * g.stage_bytes));
+          tc::tma_load_2d_2sm(sa, tmap_a, full_leader, kb * kBlockK, t.m_blk * kBlockM);
+        } else {
+          const int j0 = rm * b_slice_rows;   // this CTA's half of the tile's weight rows
+          const int grow = (j0 < g.half_rows) ? t.n_blk * g.half_rows + j0
+                                              : g.second_off + t.n_blk * g.half_rows + (j0 - g.half_rows);
+          tc::tma_load_2d_2sm(sb, tmap_b, full_leader, kb * kBlockK, grow);
+        }
+      } else if (do_a) {
+        // (non-pair) this CTA receives the whole stage (its own slices + its peers' multicasts)
+        tc::mbar_arrive_expect_tx(&bars->full[s], static_cast<uint32_t>(g.stage_bytes));
+        const int a_row0 = rn * g.a_box_rows;
+        if (g.cn > 1)
+          tc::tma_load_2d_mc(sa + a_row0 * 128, tmap_a, &bars->full[s], kb * kBlockK, t.m_blk * kBlockM + a_row0, row_mask);
+        else
+          tc::tma_load_2d(sa, tmap_a, &bars->full[s], kb * kBlockK, t.m_blk * kBlockM);
+      } else {
+        for (int b = 0; b < g.b_boxes; ++b) {
+          const int j0 = rm * b_slice_rows + b * g.b_box_rows;   // row inside the stage's B tile
+          const int grow = (j0 < g.half_rows) ? t.n_blk * g.half_rows + j0
+                                              : g.second_off + t.n_blk * g.half_rows + (j0 - g.half_rows);
+          if (g.cm > 1)
+            tc::tma_load_2d_mc(sb + j0 * 128, tmap_b, &bars->full[s], kb * kBlockK, grow, col_mask);
+          else
+            tc::tma_load_2d(sb + j0 * 128, tmap_b, &bars->full[s], kb * kBlockK, grow);
+        }
+      }
+      }
+      __syncwarp();
+      if (prof) c_issue += clock64() - t1;
       if (++s == g.stages) {
         s = 0;
         ph ^= 1u;
       }
     }
   }
+  if (prof && blockIdx.x < 256 && (threadIdx.x & 31) == 0) {
+    g_dbg_counters[blockIdx.x * 8 + 0] = c_wait;
+    g_dbg_counters[blockIdx.x * 8 + 1] = c_issue;
+    g_dbg_counters[blockIdx.x * 8 + 2] = n_iter;
+  }
 }
 
-__device__ __forceinline__ void mma_loop(uint8_t* smem, PipeBarriers* bars, const GemmShape& g, uint32_t tmem_base) {
+template <bool PAIR>
+__device__ __forceinline__ void mma_loop(uint8_t* smem, PipeBarriers* bars, const GemmShape& g, uint32_t tmem_base,
+                                         int rn, int rm) {
   const int num_kb = (g.k + kBlockK - 1) / kBlockK;
-  const int total = g.m_tiles * g.n_tiles;
-  const uint32_t idesc = tc::umma_idesc_bf16_f32(kBlockM, static_cast<uint32_t>(g.tile_n));
+  constexpr bool pair = PAIR;
+  const uint32_t idesc = tc::umma_idesc_bf16_f32(pair ? 2 * kBlockM : kBlockM, static_cast<uint32_t>(g.tile_n));
+  uint16_t sender_mask = 0;   // every CTA that writes into my smem: my cluster row and column
+  for (int j = 0; j < g.cn; ++j) sender_mask |= static_cast<uint16_t>(1u << (rm * g.cn + j));
+  for (int i = 0; i < g.cm; ++i) sender_mask |= static_cast<uint16_t>(1u << (i * g.cn + rn));
+  const bool clustered = !pair && g.cn * g.cm > 1;
   int s = 0;
   uint32_t ph = 0;
-  int it = 0;
-  for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+  TileCoord t;
+  const bool prof = (g.debug & 16) != 0;
+  long long c_acc = 0, c_full = 0, c_mma = 0, c_commit = 0;
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);   // warp-uniform for the compiler
+  for (int it = 0; tile_at(g, it, rn, rm, t); ++it) {
     const int as = it & 1;
     const uint32_t aph = (it >> 1) & 1u;
+    const long long ta = prof ? clock64() : 0;
     tc::mbar_wait(&bars->tmem_empty[as], aph ^ 1u);
     tc::fence_after_thread_sync();
+    if (prof) c_acc += clock64() - ta;
     const uint32_t d_tmem = tmem_base + as * kAccStride;
     for (int kb = 0; kb < num_kb; ++kb) {
+      const long long t0 = prof ? clock64() : 0;
       tc::mbar_wait(&bars->full[s], ph);
       tc::fence_after_thread_sync();
+      const long long t1 = prof ? clock64() : 0;
+      c_full += t1 - t0;
       const uint32_t a_addr = tc::smem_u32(smem + s * g.stage_bytes);
       const uint32_t b_addr = a_addr + kABytes;
+      const bool leader_lane = tc::elect_one();
+      if (leader_lane) {
 #pragma unroll
-      for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-        const uint64_t da = tc::umma_desc_kmajor_sw128(a_addr + k * kUmmaK * 2);
-        const uint64_t db = tc::umma_desc_kmajor_sw128(b_addr + k * kUmmaK * 2);
-        tc::umma_bf16_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+        for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+          if (g.debug & 2) break;   // profiling: no tensor work
+          const uint64_t da = tc::umma_desc_kmajor_sw128(a_addr + k * kUmmaK * 2);
+          const uint64_t db = tc::umma_desc_kmajor_sw128(b_addr + k * kUmmaK * 2);
+          if constexpr (pair)
+            tc::umma_bf16_ss_2sm(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          else
+            tc::umma_bf16_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
       }
-      tc::umma_commit(&bars->empty[s]);  // frees the smem slot once these MMAs have read it
+      const long long t2 = prof ? clock64() : 0;
+      c_mma += t2 - t1;
+      // slot free once these MMAs have read it: tell every CTA that sends into this slot
+      // (tcgen05.commit must come from the thread that issued the MMAs)
+      if (!leader_lane) {
+      } else if (g.debug & 8) {
+        tc::mbar_arrive(&bars->empty[s]);   // profiling: plain arrive instead of tcgen05.commit
+      } else if constexpr (pair) {
+        tc::umma_commit_2sm_mc(&bars->empty[s], 0x3);   // frees the slot in both CTAs of the pair
+      } else {
+        if (clustered)
+          tc::umma_commit_mc(&bars->empty[s], sender_mask);
+        else
+          tc::umma_commit(&bars->empty[s]);
+      }
+      __syncwarp();
+      if (prof) c_commit += clock64() - t2;
       if (++s == g.stages) {
         s = 0;
         ph ^= 1u;
       }
     }
-    tc::umma_commit(&bars->tmem_full[as]);  // accumulator complete -> epilogue
+    if (tc::elect_one()) {
+      if constexpr (pair)
+        tc::umma_commit_2sm_mc(&bars->tmem_full[as], 0x3);   // accumulator complete -> both epilogues
+      else
+        tc::umma_commit(&bars->tmem_full[as]);               // accumulator complete -> epilogue
+    }
+    __syncwarp();
+  }
+  if (prof && blockIdx.x < 256 && (threadIdx.x & 31) == 0) {
+    g_dbg_counters[blockIdx.x * 8 + 3] = c_acc;
+    g_dbg_counters[blockIdx.x * 8 + 4] = c_full;
+    g_dbg_counters[blockIdx.x * 8 + 5] = c_mma;
+    g_dbg_counters[blockIdx.x * 8 + 6] = c_commit;
   }
 }
 
-__device__ __forceinline__ PipeBarriers* setup_pipeline(uint8_t*& smem, const GemmShape& g, const CUtensorMap* ta,
-                                                        const CUtensorMap* tb) {
+template <bool PAIR>
+__device__ __forceinline__ PipeBarriers* setup_pipeline(uint8_t*& smem, uint8_t*& extra, const GemmShape& g,
+                                                        const CUtensorMap* ta, const CUtensorMap* tb) {
   extern __shared__ uint8_t smem_raw[];
   smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  PipeBarriers* bars = reinterpret_cast<PipeBarriers*>(smem + g.stages * g.stage_bytes);
+  extra = smem + g.stages * g.stage_bytes;
+  PipeBarriers* bars = reinterpret_cast<PipeBarriers*>(extra + g.extra_smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     tc::prefetch_tensormap(ta);
@@ -152,26 +310,49 @@ __device__ __forceinline__ PipeBarriers* setup_pipeline(uint8_t*& smem, const Ge
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < g.stages; ++i) {
       tc::mbar_init(&bars->full[i], 1);
-      tc::mbar_init(&bars->empty[i], 1);
+      tc::mbar_init(&bars->empty[i], PAIR ? 1u : static_cast<uint32_t>(g.cn + g.cm - 1));
     }
     for (int i = 0; i < 2; ++i) {
       tc::mbar_init(&bars->tmem_full[i], 1);
-      tc::mbar_init(&bars->tmem_empty[i], kEpiWarps);
+      tc::mbar_init(&bars->tmem_empty[i], PAIR ? 2 * kEpiWarps : kEpiWarps);   // pair: both CTAs' epilogues
     }
     tc::fence_mbar_init();
   }
-  if (warp == 2) tc::tmem_alloc<kTmemCols>(&bars->tmem_base);
+  if (warp == 2) {
+    if constexpr (PAIR)
+      tc::tmem_alloc_2sm<kTmemCols>(&bars->tmem_base);
+    else
+      tc::tmem_alloc<kTmemCols>(&bars->tmem_base);
+  }
   tc::fence_before_thread_sync();
   __syncthreads();
+  if (g.cn * g.cm > 1) tc::cluster_sync_all();   // peers' barriers exist before anything is multicast
   tc::fence_after_thread_sync();
   return bars;
 }
 
-__device__ __forceinline__ void teardown_pipeline(PipeBarriers* bars) {
+template <bool PAIR>
+__device__ __forceinline__ void teardown_pipeline(PipeBarriers* bars, const GemmShape& g) {
   tc::fence_before_thread_sync();
   __syncthreads();
+  if (g.cn * g.cm > 1) tc::cluster_sync_all();   // nobody exits while a peer may still signal its smem
   tc::fence_after_thread_sync();
-  if ((threadIdx.x >> 5) == 2) tc::tmem_dealloc<kTmemCols>(bars->tmem_base);
+  if ((threadIdx.x >> 5) == 2) {
+    if constexpr (PAIR)
+      tc::tmem_dealloc_2sm<kTmemCols>(bars->tmem_base);
+    else
+      tc::tmem_dealloc<kTmemCols>(bars->tmem_base);
+  }
+}
+
+// per-warp bias slices staged in shared memory: lanes load coalesced, everyone re-reads float4 broadcasts
+__device__ __forceinline__ void stage_bias(float* sb, const float* b0, const float* b1, int n, int lane) {
+  __syncwarp();
+  for (int i = lane; i < 64; i += 32) {
+    sb[i] = (b0 != nullptr && i < n) ? __ldg(b0 + i) : 0.f;
+    sb[64 + i] = (b1 != nullptr && i < n) ? __ldg(b1 + i) : 0.f;
+  }
+  __syncwarp();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -179,97 +360,149 @@ __device__ __forceinline__ void teardown_pipeline(PipeBarriers* bars) {
 // ------------------------------------------------------------------------------------------
 struct GegluArgs {
   const float* b1;                 // [2h] or null
-  const uint8_t* neuron_override;  // [h] or null
+  const uint8_t* neuron_override;  // [h] or null          (FEAT path)
   float override_value;
-  __nv_bfloat16* H;                // [T, h]
   float* scores;                   // [T, E] or null
-  __nv_bfloat16* gate_out;         // [T, h] or null
+  __nv_bfloat16* gate_out;         // [T, h] or null       (FEAT path)
   int h, E, es, nv;                // nv = neuron pairs per tile (tile_n = 2 nv)
 };
 
-template <int CH, int ACT>
-__device__ __forceinline__ void geglu_epilogue_tile(const GegluArgs& a, uint32_t taddr, int row, bool row_ok,
-                                                    int n_tile0, int col_begin, int col_end) {
-  // this thread owns token `row`; columns [col_begin, col_end) of the tile are whole experts
-  for (int c0 = col_begin; c0 < col_end; c0 += a.es) {
-    float score = 0.f;
-    const int n_exp = n_tile0 + c0;  // first packed neuron of this expert
-    for (int c = 0; c < a.es; c += CH) {
-      uint32_t v[CH], g[CH];
-      tc::tmem_ld_cols<CH>(taddr + c0 + c, v);
-      tc::tmem_ld_cols<CH>(taddr + a.nv + c0 + c, g);
-      tc::tmem_ld_wait();
-      const int n = n_exp + c;
-      uint32_t hw[CH / 2], gw[CH / 2];
+// One column group (cpg = nv / 4 neuron pairs) of one tile for the token row this thread owns.
+// CH divides both cpg and es, so a chunk never straddles an expert.
+template <int CH, int ACT, bool FEAT>
+__device__ __forceinline__ void geglu_epilogue_group(const GegluArgs& a, uint32_t taddr, const float* sbias,
+                                                     __nv_bfloat16* hrow_smem, float* spart, int row, bool row_ok,
+                                                     int n_tile0, int col0, int cpg, int q_row) {
+  float score = 0.f;
+  for (int c = 0; c < cpg; c += CH) {
+    uint32_t v[CH], g[CH];
+    tc::tmem_ld_cols<CH>(taddr + col0 + c, v);
+    tc::tmem_ld_cols<CH>(taddr + a.nv + col0 + c, g);
+    tc::tmem_ld_wait();
+    const int n = n_tile0 + col0 + c;   // first packed neuron of this chunk
+    uint32_t hw[CH / 2];
+    uint32_t gw[FEAT ? CH / 2 : 1];
 #pragma unroll
-      for (int i = 0; i < CH; i += 2) {
-        float g0 = __uint_as_float(g[i]), g1 = __uint_as_float(g[i + 1]);
-        float v0 = __uint_as_float(v[i]), v1 = __uint_as_float(v[i + 1]);
-        if (a.b1 != nullptr) {
-          g0 += __ldg(a.b1 + a.h + n + i);
-          g1 += __ldg(a.b1 + a.h + n + i + 1);
-          v0 += __ldg(a.b1 + n + i);
-          v1 += __ldg(a.b1 + n + i + 1);
+    for (int i = 0; i < CH; i += 4) {
+      const float4 bv = *reinterpret_cast<const float4*>(sbias + c + i);
+      const float4 bg = *reinterpret_cast<const float4*>(sbias + 64 + c + i);
+      float gg[4] = {__uint_as_float(g[i]) + bg.x, __uint_as_float(g[i + 1]) + bg.y, __uint_as_float(g[i + 2]) + bg.z,
+                     __uint_as_float(g[i + 3]) + bg.w};
+      const float vv[4] = {__uint_as_float(v[i]) + bv.x, __uint_as_float(v[i + 1]) + bv.y,
+                           __uint_as_float(v[i + 2]) + bv.z, __uint_as_float(v[i + 3]) + bv.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        gg[j] = activate<ACT>(gg[j]);
+        if constexpr (FEAT) {
+          if (a.neuron_override != nullptr && __ldg(a.neuron_override + n + i + j)) gg[j] = a.override_value;
         }
-        g0 = activate<ACT>(g0);
-        g1 = activate<ACT>(g1);
-        if (a.neuron_override != nullptr) {
-          if (__ldg(a.neuron_override + n + i)) g0 = a.override_value;
-          if (__ldg(a.neuron_override + n + i + 1)) g1 = a.override_value;
-        }
-        score += g0;
-        score += g1;
-        hw[i / 2] = pack_bf16x2(v0 * g0, v1 * g1);
-        gw[i / 2] = pack_bf16x2(g0, g1);
+        score += gg[j];
       }
-      if (row_ok) {
-        store_words<CH / 2>(a.H + static_cast<size_t>(row) * a.h + n, hw);
-        if (a.gate_out != nullptr) store_words<CH / 2>(a.gate_out + static_cast<size_t>(row) * a.h + n, gw);
+      hw[i / 2] = pack_bf16x2(vv[0] * gg[0], vv[1] * gg[1]);
+      hw[i / 2 + 1] = pack_bf16x2(vv[2] * gg[2], vv[3] * gg[3]);
+      if constexpr (FEAT) {
+        gw[i / 2] = pack_bf16x2(gg[0], gg[1]);
+        gw[i / 2 + 1] = pack_bf16x2(gg[2], gg[3]);
       }
     }
-    if (a.scores != nullptr && row_ok) a.scores[static_cast<size_t>(row) * a.E + n_exp / a.es] = score;
+    store_words<CH / 2>(hrow_smem + col0 + c, hw);   // staged; one TMA store per tile writes it out
+    if constexpr (FEAT) {
+      if (a.gate_out != nullptr && row_ok) store_words<CH / 2>(a.gate_out + static_cast<size_t>(row) * a.h + n, gw);
+    }
+    // expert boundary inside the group (es < cpg): flush the finished expert's score
+    if (a.es < cpg && ((c + CH) % a.es) == 0) {
+      if (a.scores != nullptr && row_ok) a.scores[static_cast<size_t>(row) * a.E + (n + CH - a.es) / a.es] = score;
+      score = 0.f;
+    }
+  }
+  if (a.es >= cpg && a.scores != nullptr) {
+    if (a.es == cpg) {
+      if (row_ok) a.scores[static_cast<size_t>(row) * a.E + (n_tile0 + col0) / a.es] = score;
+    } else {
+      // one expert spans `span` adjacent column groups: combine the partial sums through smem
+      const int span = a.es / cpg, cg = col0 / cpg;
+      spart[q_row * kColGroups + cg] = score;
+      tc::named_bar_sync(2 + (q_row >> 5), 4 * 32);   // the 4 warps of this lane quarter
+      if ((cg % span) == 0 && row_ok) {
+        float tot = 0.f;
+        for (int j = 0; j < span; ++j) tot += spart[q_row * kColGroups + cg + j];
+        a.scores[static_cast<size_t>(row) * a.E + (n_tile0 + col0) / a.es] = tot;
+      }
+    }
   }
 }
 
-template <int CH>
+template <int CH, bool FEAT, bool PAIR>
 __global__ void __launch_bounds__(kNumThreads, 1)
 geglu_up_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w1,
-                const GemmShape g, const GegluArgs a, const int act) {
-  uint8_t* smem;
-  PipeBarriers* bars = setup_pipeline(smem, g, &tmap_x, &tmap_w1);
+                const __grid_constant__ CUtensorMap tmap_h, const GemmShape g, const GegluArgs a, const int act) {
+  uint8_t *smem, *extra;
+  PipeBarriers* bars = setup_pipeline<PAIR>(smem, extra, g, &tmap_x, &tmap_w1);
   const uint32_t tmem_base = bars->tmem_base;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int crank = static_cast<int>(tc::cluster_ctarank());
+  const int rn = crank % g.cn, rm = crank / g.cn;
 
-  if (warp == 0) {
-    if (lane == 0) producer_loop<true>(&tmap_x, &tmap_w1, smem, bars, g, a.h);
+  if (warp == 0 || warp == 3) {
+    producer_loop<PAIR>(&tmap_x, &tmap_w1, smem, bars, g, rn, rm, warp == 0);   // warp-converged; one elected lane issues
   } else if (warp == 1) {
-    if (lane == 0) mma_loop(smem, bars, g, tmem_base);
+    if (!PAIR || rm == 0) mma_loop<PAIR>(smem, bars, g, tmem_base, rn, rm);   // pair: the leader CTA issues for both
   } else if (warp >= kEpiWarp0) {
-    const int q = warp & 3;                      // TMEM lane quarter this warp may access
-    const int cg = (warp - kEpiWarp0) >> 2;      // column group (0/1)
-    const int cols_per_group = a.nv / 2;
-    const int total = g.m_tiles * g.n_tiles;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
-      const int m_blk = tile / g.n_tiles, n_blk = tile % g.n_tiles;
+    const int ew = warp - kEpiWarp0;
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int cg = ew >> 2;            // column group 0..3
+    const int cpg = a.nv / kColGroups;
+    // epilogue smem: [2][128][nv] bf16 H staging | per-warp bias | partial scores
+    __nv_bfloat16* hstage = reinterpret_cast<__nv_bfloat16*>(extra);
+    float* sbias = reinterpret_cast<float*>(extra + 2 * kBlockM * a.nv * 2) + ew * (kBiasSmemPerWarp / 4);
+    float* spart = reinterpret_cast<float*>(extra + 2 * kBlockM * a.nv * 2 + kEpiWarps * kBiasSmemPerWarp);
+    const bool store_thread = (ew == 0 && lane == 0);
+    if (store_thread) tc::prefetch_tensormap(&tmap_h);
+    const int q_row = 32 * q + lane;
+    TileCoord t;
+    for (int it = 0; tile_at(g, it, rn, rm, t); ++it) {
       const int as = it & 1;
       const uint32_t aph = (it >> 1) & 1u;
+      const int n_tile0 = t.n_blk * a.nv;
+      const int col0 = cg * cpg;
+      stage_bias(sbias, a.b1 != nullptr ? a.b1 + n_tile0 + col0 : nullptr,
+                 a.b1 != nullptr ? a.b1 + a.h + n_tile0 + col0 : nullptr, cpg, lane);
       tc::mbar_wait(&bars->tmem_full[as], aph);
       tc::fence_after_thread_sync();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + as * kAccStride;
-      const int row = m_blk * kBlockM + 32 * q + lane;
+      const int row = t.m_blk * kBlockM + q_row;
       const bool row_ok = row < g.rows;
-      const int cb = cg * cols_per_group, ce = cb + cols_per_group;
-      if (act == MOE_ACT_GELU)
-        geglu_epilogue_tile<CH, MOE_ACT_GELU>(a, taddr, row, row_ok, n_blk * a.nv, cb, ce);
+      __nv_bfloat16* hbuf = hstage + (it & 1) * kBlockM * a.nv;
+      if (g.debug & 4) {
+      } else if (act == MOE_ACT_GELU)
+        geglu_epilogue_group<CH, MOE_ACT_GELU, FEAT>(a, taddr, sbias, hbuf + q_row * a.nv, spart, row, row_ok, n_tile0,
+                                                     col0, cpg, q_row);
       else
-        geglu_epilogue_tile<CH, MOE_ACT_RELU>(a, taddr, row, row_ok, n_blk * a.nv, cb, ce);
+        geglu_epilogue_group<CH, MOE_ACT_RELU, FEAT>(a, taddr, sbias, hbuf + q_row * a.nv, spart, row, row_ok, n_tile0,
+                                                     col0, cpg, q_row);
+      // accumulator stage drained -> MMA may overwrite it
       tc::fence_before_thread_sync();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&bars->tmem_empty[as]);
+      if (lane == 0) {
+        if constexpr (PAIR)
+          tc::mbar_arrive_cluster(tc::mapa_u32(&bars->tmem_empty[as], 0));   // the leader's MMA thread waits
+        else
+          tc::mbar_arrive(&bars->tmem_empty[as]);
+      }
+      // H tile: generic-proxy smem writes -> async proxy, then one TMA store for the whole tile.
+      // The store thread first waits until the previous tile's store has finished READING its
+      // buffer, so after the barrier everybody may overwrite that buffer in the next iteration.
+      tc::fence_proxy_async_smem();
+      if (store_thread) tc::tma_store_wait_read<0>();
+      tc::named_bar_sync(kEpiBarrierId, kEpiThreads);
+      if (store_thread) {
+        tc::tma_store_2d(&tmap_h, hbuf, n_tile0, t.m_blk * kBlockM);   // rows beyond T are clipped
+        tc::tma_store_commit();
+      }
     }
+    if (store_thread) tc::tma_store_wait<0>();
   }
-  teardown_pipeline(bars);
+  teardown_pipeline<PAIR>(bars, g);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -281,107 +514,229 @@ struct DownArgs {
   int d;
 };
 
-template <int CH>
+template <int CH, bool PAIR>
 __global__ void __launch_bounds__(kNumThreads, 1)
 down_proj_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant__ CUtensorMap tmap_w2,
                  const GemmShape g, const DownArgs a) {
-  uint8_t* smem;
-  PipeBarriers* bars = setup_pipeline(smem, g, &tmap_h, &tmap_w2);
+  uint8_t *smem, *extra;
+  PipeBarriers* bars = setup_pipeline<PAIR>(smem, extra, g, &tmap_h, &tmap_w2);
   const uint32_t tmem_base = bars->tmem_base;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int crank = static_cast<int>(tc::cluster_ctarank());
+  const int rn = crank % g.cn, rm = crank / g.cn;
 
-  if (warp == 0) {
-    if (lane == 0) producer_loop<false>(&tmap_h, &tmap_w2, smem, bars, g, 0);
+  if (warp == 0 || warp == 3) {
+    producer_loop<PAIR>(&tmap_h, &tmap_w2, smem, bars, g, rn, rm, warp == 0);   // warp-converged; one elected lane issues
   } else if (warp == 1) {
-    if (lane == 0) mma_loop(smem, bars, g, tmem_base);
+    if (!PAIR || rm == 0) mma_loop<PAIR>(smem, bars, g, tmem_base, rn, rm);   // pair: the leader CTA issues for both
   } else if (warp >= kEpiWarp0) {
+    const int ew = warp - kEpiWarp0;
     const int q = warp & 3;
-    const int cg = (warp - kEpiWarp0) >> 2;
-    const int cols_per_group = g.tile_n / 2;
-    const int total = g.m_tiles * g.n_tiles;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
-      const int m_blk = tile / g.n_tiles, n_blk = tile % g.n_tiles;
+    const int cg = ew >> 2;
+    const int cpg = g.tile_n / kColGroups;
+    float* sbias = reinterpret_cast<float*>(extra) + ew * (kBiasSmemPerWarp / 4);
+    TileCoord t;
+    for (int it = 0; tile_at(g, it, rn, rm, t); ++it) {
       const int as = it & 1;
       const uint32_t aph = (it >> 1) & 1u;
+      const int n0 = t.n_blk * g.tile_n + cg * cpg;    // first output column of this warp's group
+      const int nvalid = max(0, min(cpg, a.d - n0));   // the last tile may overhang d
+      stage_bias(sbias, a.b2 != nullptr ? a.b2 + n0 : nullptr, nullptr, nvalid, lane);
       tc::mbar_wait(&bars->tmem_full[as], aph);
       tc::fence_after_thread_sync();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + as * kAccStride;
-      const int row = m_blk * kBlockM + 32 * q + lane;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + as * kAccStride + cg * cpg;
+      const int row = t.m_blk * kBlockM + 32 * q + lane;
       const bool row_ok = row < g.rows;
-      for (int c = cg * cols_per_group; c < (cg + 1) * cols_per_group; c += CH) {
+      for (int c = 0; c < cpg; c += CH) {
+        if (g.debug & 4) break;
         uint32_t acc[CH];
         tc::tmem_ld_cols<CH>(taddr + c, acc);
         tc::tmem_ld_wait();
-        const int n = n_blk * g.tile_n + c;
         uint32_t yw[CH / 2];
 #pragma unroll
-        for (int i = 0; i < CH; i += 2) {
-          float y0 = __uint_as_float(acc[i]), y1 = __uint_as_float(acc[i + 1]);
-          if (a.b2 != nullptr) {  // indices clamped: the last tile may overhang d
-            y0 += __ldg(a.b2 + min(n + i, a.d - 1));
-            y1 += __ldg(a.b2 + min(n + i + 1, a.d - 1));
-          }
-          yw[i / 2] = pack_bf16x2(y0, y1);
+        for (int i = 0; i < CH; i += 4) {
+          const float4 b = *reinterpret_cast<const float4*>(sbias + c + i);
+          yw[i / 2] = pack_bf16x2(__uint_as_float(acc[i]) + b.x, __uint_as_float(acc[i + 1]) + b.y);
+          yw[i / 2 + 1] = pack_bf16x2(__uint_as_float(acc[i + 2]) + b.z, __uint_as_float(acc[i + 3]) + b.w);
         }
         if (row_ok) {
-          __nv_bfloat16* dst = a.Y + static_cast<size_t>(row) * a.d + n;
-          if (n + CH <= a.d) {
+          __nv_bfloat16* dst = a.Y + static_cast<size_t>(row) * a.d + n0 + c;
+          if (c + CH <= nvalid) {
             store_words<CH / 2>(dst, yw);
-          } else {  // last tile of a d that is not a multiple of the tile width
+          } else {
 #pragma unroll
             for (int i = 0; i < CH / 2; ++i)
-              if (n + 2 * i < a.d) *reinterpret_cast<uint32_t*>(dst + 2 * i) = yw[i];
+              if (c + 2 * i < nvalid) *reinterpret_cast<uint32_t*>(dst + 2 * i) = yw[i];
           }
         }
       }
       tc::fence_before_thread_sync();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&bars->tmem_empty[as]);
+      if (lane == 0) {
+        if constexpr (PAIR)
+          tc::mbar_arrive_cluster(tc::mapa_u32(&bars->tmem_empty[as], 0));   // the leader's MMA thread waits
+        else
+          tc::mbar_arrive(&bars->tmem_empty[as]);
+      }
     }
   }
-  teardown_pipeline(bars);
+  teardown_pipeline<PAIR>(bars, g);
 }
 
 // ------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------
-static int fill_shape(GemmShape& g, int rows, int k, int n_total, int tile_n, int b_rows) {
-  g.rows = rows;
-  g.k = k;
-  g.m_tiles = (rows + kBlockM - 1) / kBlockM;
-  g.n_tiles = (n_total + b_rows - 1) / b_rows;
-  g.tile_n = tile_n;
-  g.b_rows = b_rows;
-  g.stage_bytes = kABytes + tile_n * 128;
-  int stages = (kSmemLimit - 1024 - static_cast<int>(sizeof(PipeBarriers))) / g.stage_bytes;
+struct ClusterChoice {
+  int cn, cm;
+};
+
+// L2->SM bandwidth and tensor rate used by the tiling heuristics (measured on B200)
+constexpr double kL2BytesPerCycle = 3600.0;   // ~6.8 TB/s at 1.9 GHz, whole chip
+static double mma_cycles_per_kstep(int tile_n) {
+  const double tensor = tile_n / 2.0;                       // 128 x N x 16 at 4096 MAC/cycle/SM
+  const double smem = (4096.0 + 32.0 * tile_n) / 128.0;     // A + B operand bytes at 128 B/cycle
+  return tensor > smem ? tensor : smem;
+}
+
+static bool env_cluster(const char* name, ClusterChoice& c) {
+  const char* e = getenv(name);
+  if (!e) return false;
+  int a = 0, b = 0;
+  if (sscanf(e, "%d,%d", &a, &b) != 2 || a < 1 || b < 1 || a * b > 8) return false;
+  c.cn = a;
+  c.cm = b;
+  return true;
+}
+
+// Pick the cluster shape minimising max(tensor time over waves, panel traffic / L2 bandwidth).
+static ClusterChoice choose_cluster(const char* env, int m_tiles, int n_tiles, int tile_n, int half_rows, int k,
+                                    double epi_cycles_per_tile) {
+  ClusterChoice forced = {1, 1};
+  const int cands[8][2] = {{1, 1}, {2, 1}, {1, 2}, {2, 2}, {4, 1}, {1, 4}, {4, 2}, {2, 4}};
+  // Measured on B200 (profiles/r01_sweep_cluster.log): multicast does not pay -- the kernels are bound by the
+  // single-thread TMA / MMA issue loops, not by L2 reads -- so it is used only when forced through `env`.
+  const bool have_forced = env_cluster(env, forced);
+  if (!have_forced) return ClusterChoice{1, 1};
+  const int sms = sm_count();
+  ClusterChoice best = {1, 1};
+  double best_t = 1e300;
+  for (auto& cd : cands) {
+    const int cn = cd[0], cm = cd[1];
+    if (have_forced && (cn != forced.cn || cm != forced.cm)) continue;
+    if (n_tiles % cn) continue;                         // weight rows beyond N must never be addressed
+    if (kBlockM % (8 * cn)) continue;
+    const int slice = tile_n / cm;
+    if (tile_n % cm || slice % 8) continue;             // 8-row swizzle groups stay whole
+    if (slice > half_rows ? (slice % half_rows) : (half_rows % slice)) continue;   // boxes do not straddle halves
+    if ((slice > half_rows ? half_rows : slice) > 256) continue;
+    const int csize = cn * cm;
+    const int n_clusters = sms / csize;
+    if (n_clusters < 1) continue;
+    const long long ctiles = static_cast<long long>((m_tiles + cm - 1) / cm) * (n_tiles / cn);
+    const long long rounds = (ctiles + n_clusters - 1) / n_clusters;
+    const double ksteps = (k + kUmmaK - 1) / kUmmaK;
+    const double per_tile = ksteps * mma_cycles_per_kstep(tile_n);
+    const double compute = rounds * (per_tile > epi_cycles_per_tile ? per_tile : epi_cycles_per_tile);
+    const double bytes = static_cast<double>(ctiles) * (cm * kBlockM + cn * tile_n) * k * 2.0;
+    const double traffic = bytes / kL2BytesPerCycle;
+    // multicast is not free (cluster barriers, lock-step): 3 % per doubling as a tie-breaker
+    double t = compute > traffic ? compute : traffic;
+    for (int c = csize; c > 1; c >>= 1) t *= 1.03;
+    if (t < best_t) {
+      best_t = t;
+      best = {cn, cm};
+    }
+  }
+  return best;
+}
+
+// cta_group::2 pairs unless MOE_PAIR=0
+static bool pair_enabled() {
+  const char* e = getenv("MOE_PAIR");
+  return !(e && atoi(e) == 0);
+}
+
+static int debug_mode() {
+  const char* e = getenv("MOE_DEBUG_MODE");
+  return e ? atoi(e) : 0;
+}
+
+static int finish_shape(GemmShape& g, int extra_smem) {
+  g.debug = debug_mode();
+  g.a_box_rows = kBlockM / g.cn;
+  const int slice = g.tile_n / g.cm;
+  g.b_box_rows = slice < g.half_rows ? slice : g.half_rows;
+  g.b_boxes = slice / g.b_box_rows;
+  g.m_ctiles = (g.m_tiles + g.cm - 1) / g.cm;
+  g.n_ctiles = g.n_tiles / g.cn;
+  g.stage_bytes = kABytes + (g.pair ? g.tile_n / 2 : g.tile_n) * 128;
+  g.extra_smem = extra_smem;
+  int stages = (kSmemLimit - 1024 - extra_smem - static_cast<int>(sizeof(PipeBarriers))) / g.stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
+  if (const char* e = getenv("MOE_DEBUG_STAGES")) {
+    const int cap = atoi(e);
+    if (cap >= 2 && cap < stages) stages = cap;
+  }
   if (stages < 2) return -1;
   g.stages = stages;
   return 0;
 }
 
 static size_t smem_bytes(const GemmShape& g) {
-  return static_cast<size_t>(g.stages) * g.stage_bytes + 1024 + sizeof(PipeBarriers);
+  return static_cast<size_t>(g.stages) * g.stage_bytes + 1024 + g.extra_smem + sizeof(PipeBarriers);
 }
 
 // opt in to the full 227 KiB of dynamic shared memory, once per kernel (keyed by entry address:
 // all instantiations of one template share a function-pointer TYPE)
 static int ensure_smem(const void* kfn, size_t bytes) {
-  static const void* configured[32];
+  static const void* configured[64];
   static int n_configured = 0;
   if (bytes > static_cast<size_t>(kSmemLimit)) return fail(MOE_ERR_UNSUPPORTED_SHAPE, "smem request %zu too large", bytes);
   for (int i = 0; i < n_configured; ++i)
     if (configured[i] == kfn) return MOE_OK;
   cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
   if (e != cudaSuccess) return fail(MOE_ERR_CUDA, "cudaFuncSetAttribute(smem=%d): %s", kSmemLimit, cudaGetErrorString(e));
-  if (n_configured < 32) configured[n_configured++] = kfn;
+  if (n_configured < 64) configured[n_configured++] = kfn;
+  return MOE_OK;
+}
+
+template <typename... KArgs, typename... Args>
+static int launch_clustered(void (*kernel)(KArgs...), const GemmShape& g, cudaStream_t st, Args&&... args) {
+  const size_t smem = smem_bytes(g);
+  int rc = ensure_smem(reinterpret_cast<const void*>(kernel), smem);
+  if (rc) return rc;
+  const int csize = g.cn * g.cm;
+  const long long ctiles = static_cast<long long>(g.m_ctiles) * g.n_ctiles;
+  long long n_clusters = sm_count() / csize;
+  if (n_clusters > ctiles) n_clusters = ctiles;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(n_clusters * csize));
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = static_cast<unsigned>(csize);
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+  if (e != cudaSuccess) return fail(MOE_ERR_CUDA, "cudaLaunchKernelEx(cluster %dx%d): %s", g.cn, g.cm, cudaGetErrorString(e));
   return MOE_OK;
 }
 
 }  // namespace moe
 
 extern "C" {
+
+int moe_debug_counters(unsigned long long* host_out, int n) {
+  using namespace moe;
+  MOE_REQUIRE(host_out != nullptr && n >= 0 && n <= 256 * 8, MOE_ERR_INVALID_ARGUMENT, "moe_debug_counters: bad args");
+  cudaError_t e = cudaMemcpyFromSymbol(host_out, g_dbg_counters, sizeof(unsigned long long) * n);
+  if (e != cudaSuccess) return fail(MOE_ERR_CUDA, "moe_debug_counters: %s", cudaGetErrorString(e));
+  return MOE_OK;
+}
 
 int moe_geglu_up(const void* x, const void* w1p, const float* b1p, const uint8_t* neuron_override,
                  float override_value, void* H, float* scores, void* gate_out, int T, int d, int h, int E,
@@ -393,50 +748,80 @@ int moe_geglu_up(const void* x, const void* w1p, const float* b1p, const uint8_t
   MOE_REQUIRE(static_cast<long long>(E) * es == h, MOE_ERR_INVALID_ARGUMENT, "moe_geglu_up: E*es=%d*%d != h=%d", E, es, h);
   MOE_REQUIRE(d % 8 == 0 && h % 8 == 0, MOE_ERR_UNSUPPORTED_SHAPE, "moe_geglu_up: d=%d and h=%d must be multiples of 8", d, h);
   MOE_REQUIRE(act == MOE_ACT_GELU || act == MOE_ACT_RELU, MOE_ERR_INVALID_ARGUMENT, "moe_geglu_up: act=%d", act);
-  MOE_REQUIRE(es % 4 == 0 && es <= 64, MOE_ERR_UNSUPPORTED_SHAPE,
-              "moe_geglu_up: expert size %d unsupported (needs es %% 4 == 0 and es <= 64)", es);
+  MOE_REQUIRE(es % 4 == 0, MOE_ERR_UNSUPPORTED_SHAPE, "moe_geglu_up: expert size %d unsupported (needs es %% 4 == 0)", es);
   MOE_REQUIRE(((reinterpret_cast<uintptr_t>(H) | reinterpret_cast<uintptr_t>(gate_out)) & 15) == 0,
               MOE_ERR_INVALID_ARGUMENT, "moe_geglu_up: H / gate_out must be 16-byte aligned");
   if (T == 0) return MOE_OK;
-  // neuron pairs per tile: a multiple of 2*es (two epilogue column groups of whole experts) and of 8,
-  // dividing h, at most 128 (UMMA N = 2*nv <= 256); largest wins.
+  // nv neuron pairs per tile (UMMA N = 2 nv <= 256) split over 4 epilogue column groups of cpg = nv/4:
+  // a group holds whole experts (cpg % es == 0) or an expert spans 2 or 4 groups inside the tile.
   int nv = 0;
-  for (int cand = 128; cand >= 8; cand -= 8)
-    if (cand % (2 * es) == 0 && h % cand == 0) {
+  for (int cand = 128; cand >= 16; cand -= 8) {
+    if (h % cand || cand % 4) continue;
+    const int cpg = cand / kColGroups;
+    if (cpg % 4 || cpg > 64) continue;
+    const bool whole = cpg % es == 0;
+    const bool spans = es % cpg == 0 && (es / cpg == 2 || es / cpg == 4) && cand % es == 0;
+    if (whole || spans) {
       nv = cand;
       break;
     }
-  MOE_REQUIRE(nv > 0, MOE_ERR_UNSUPPORTED_SHAPE, "moe_geglu_up: no tile width for es=%d h=%d", es, h);
-  const int ch = (es % 32 == 0) ? 32 : (es % 20 == 0) ? 20 : (es % 16 == 0) ? 16 : (es % 8 == 0) ? 8 : 4;
+  }
+  MOE_REQUIRE(nv > 0, MOE_ERR_UNSUPPORTED_SHAPE, "moe_geglu_up: expert size %d unsupported for h=%d (no tile width)", es, h);
+  const int cpg = nv / kColGroups;
+  int gcd_v = cpg, tmp = es;
+  while (tmp) {
+    const int r = gcd_v % tmp;
+    gcd_v = tmp;
+    tmp = r;
+  }
+  const int ch = (gcd_v % 32 == 0) ? 32 : (gcd_v % 20 == 0) ? 20 : (gcd_v % 16 == 0) ? 16 : (gcd_v % 8 == 0) ? 8 : 4;
 
-  GemmShape g;
-  MOE_REQUIRE(fill_shape(g, T, d, h, 2 * nv, nv) == 0, MOE_ERR_UNSUPPORTED_SHAPE, "moe_geglu_up: tile does not fit smem");
-  CUtensorMap tx, tw;
-  int rc = make_tmap_bf16_2d(&tx, x, static_cast<uint64_t>(T), static_cast<uint64_t>(d), kBlockM, kBlockK);
+  GemmShape g = {};
+  g.rows = T;
+  g.k = d;
+  g.m_tiles = (T + kBlockM - 1) / kBlockM;
+  g.n_tiles = h / nv;
+  g.tile_n = 2 * nv;
+  g.half_rows = nv;
+  g.second_off = h;
+  ClusterChoice forced_cc;
+  if (g.m_tiles >= 2 && pair_enabled() && !env_cluster("MOE_K1_CLUSTER", forced_cc)) {
+    // cta_group::2: CTA 0 of the pair stages the value rows, CTA 1 the gate rows of the tile's weights
+    g.pair = 1;
+    g.cn = 1;
+    g.cm = 2;
+  } else {
+    // epilogue issue cycles per tile and scheduler: 4 warps x nv/4 neuron pairs x ~19 slots
+    const ClusterChoice cc = choose_cluster("MOE_K1_CLUSTER", g.m_tiles, g.n_tiles, g.tile_n, nv, d, 19.0 * nv);
+    g.cn = cc.cn;
+    g.cm = cc.cm;
+  }
+  const int extra = 2 * kBlockM * nv * 2 + kEpiWarps * kBiasSmemPerWarp + kBlockM * kColGroups * 4;
+  MOE_REQUIRE(finish_shape(g, extra) == 0, MOE_ERR_UNSUPPORTED_SHAPE, "moe_geglu_up: tile does not fit smem");
+  CUtensorMap tx, tw, th;
+  int rc = make_tmap_bf16_2d(&tx, x, static_cast<uint64_t>(T), static_cast<uint64_t>(d), static_cast<uint32_t>(g.a_box_rows), kBlockK);
   if (rc) return rc;
-  rc = make_tmap_bf16_2d(&tw, w1p, static_cast<uint64_t>(2) * h, static_cast<uint64_t>(d), static_cast<uint32_t>(nv), kBlockK);
+  rc = make_tmap_bf16_2d(&tw, w1p, static_cast<uint64_t>(2) * h, static_cast<uint64_t>(d), static_cast<uint32_t>(g.b_box_rows), kBlockK);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&th, H, static_cast<uint64_t>(T), static_cast<uint64_t>(h), kBlockM, static_cast<uint32_t>(nv), false);
   if (rc) return rc;
   GegluArgs a;
   a.b1 = b1p;
   a.neuron_override = neuron_override;
   a.override_value = override_value;
-  a.H = static_cast<__nv_bfloat16*>(H);
   a.scores = scores;
   a.gate_out = static_cast<__nv_bfloat16*>(gate_out);
   a.h = h;
   a.E = E;
   a.es = es;
   a.nv = nv;
-  const int total = g.m_tiles * g.n_tiles;
-  const int grid = total < sm_count() ? total : sm_count();
-  const size_t smem = smem_bytes(g);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define MOE_LAUNCH_GEGLU(CHV)                                              \
-  do {                                                                     \
-    rc = ensure_smem(reinterpret_cast<const void*>(&geglu_up_kernel<CHV>), smem);                          \
-    if (rc) return rc;                                                     \
-    geglu_up_kernel<CHV><<<grid, kNumThreads, smem, st>>>(tx, tw, g, a, act); \
-  } while (0)
+  const bool feat = neuron_override != nullptr || gate_out != nullptr;
+#define MOE_LAUNCH_GEGLU(CHV)                                                                              \
+  rc = g.pair ? (feat ? launch_clustered(geglu_up_kernel<CHV, true, true>, g, st, tx, tw, th, g, a, act)   \
+                      : launch_clustered(geglu_up_kernel<CHV, false, true>, g, st, tx, tw, th, g, a, act)) \
+              : (feat ? launch_clustered(geglu_up_kernel<CHV, true, false>, g, st, tx, tw, th, g, a, act)  \
+                      : launch_clustered(geglu_up_kernel<CHV, false, false>, g, st, tx, tw, th, g, a, act))
   switch (ch) {
     case 32: MOE_LAUNCH_GEGLU(32); break;
     case 20: MOE_LAUNCH_GEGLU(20); break;
@@ -445,6 +830,7 @@ int moe_geglu_up(const void* x, const void* w1p, const float* b1p, const uint8_t
     default: MOE_LAUNCH_GEGLU(4); break;
   }
 #undef MOE_LAUNCH_GEGLU
+  if (rc) return rc;
   return check_launch("moe_geglu_up");
 }
 
@@ -455,54 +841,76 @@ int moe_down_proj(const void* H, const void* w2p, const float* b2, void* Y, int 
   MOE_REQUIRE(h % 8 == 0 && d % 8 == 0, MOE_ERR_UNSUPPORTED_SHAPE, "moe_down_proj: h=%d and d=%d must be multiples of 8", h, d);
   MOE_REQUIRE((reinterpret_cast<uintptr_t>(Y) & 15) == 0, MOE_ERR_INVALID_ARGUMENT, "moe_down_proj: Y must be 16-byte aligned");
   if (T == 0) return MOE_OK;
-  // tile width: a multiple of 16, <= 256 (the last tile may overhang d: TMA zero-fills the missing
-  // weight rows and the epilogue guards its stores); pick the best wave-quantised cost
+  // tile width: a multiple of 16, <= 256 (the last tile may overhang d by < 16 columns: TMA zero-fills
+  // the missing weight rows and the epilogue guards its stores).  Work units are CTA pairs (cta_group::2,
+  // 256 token rows) when there are at least two row tiles.  Per 16-wide K step the issuing thread needs
+  // ~90 cycles, the tensor pipe bn/2; among equal costs prefer more, narrower tiles (more SMs busy).
   const int m_tiles = (T + kBlockM - 1) / kBlockM;
   const int sms = sm_count();
+  ClusterChoice forced_cc = {1, 1};
+  const bool forced = env_cluster("MOE_K3_CLUSTER", forced_cc);
+  const bool pair = m_tiles >= 2 && pair_enabled() && !forced;
+  const int units = pair ? sms / 2 : sms;
+  const int m_units = pair ? (m_tiles + 1) / 2 : m_tiles;
   int best = 0;
-  double best_cost = 1e30;
+  double best_cost = 1e300;
   for (int bn = 256; bn >= 16; bn -= 16) {
-    if (bn - (d % bn ? d % bn : bn) >= 16) continue;  // never waste a whole 16-column group
-    const long long tiles = static_cast<long long>(m_tiles) * ((d + bn - 1) / bn);
-    const long long waves = (tiles + sms - 1) / sms;
-    // per-tile MMA time ~ max(bn/2, smem-bound (4096 + 32 bn)/128) cycles per K step
-    const double per_tile = bn / 2.0 > (4096.0 + 32.0 * bn) / 128.0 ? bn / 2.0 : (4096.0 + 32.0 * bn) / 128.0;
-    const double cost = waves * per_tile;
-    if (cost < best_cost - 1e-9) {
+    if (bn - (d % bn ? d % bn : bn) >= 16) continue;
+    if (pair && (bn / 2) % 8) continue;                  // each CTA of a pair stages bn/2 weight rows
+    const long long tiles = static_cast<long long>(m_units) * ((d + bn - 1) / bn);
+    const long long rounds = (tiles + units - 1) / units;
+    const double per_kstep = bn / 2.0 > 90.0 ? bn / 2.0 : 90.0;
+    const double cost = rounds * ((h + kUmmaK - 1) / kUmmaK) * per_kstep + 2000.0 * rounds;   // + epilogue / ramp
+    if (cost < best_cost * 0.999) {
       best_cost = cost;
       best = bn;
     }
   }
+  ClusterChoice best_cc = forced ? forced_cc : ClusterChoice{1, 1};
+  if (pair) best_cc = ClusterChoice{1, 2};
   MOE_REQUIRE(best > 0, MOE_ERR_UNSUPPORTED_SHAPE, "moe_down_proj: no tile width for d=%d", d);
-  const int half = best / 2;
-  const int ch = (half % 32 == 0) ? 32 : (half % 16 == 0) ? 16 : 8;
-  GemmShape g;
-  MOE_REQUIRE(fill_shape(g, T, h, d, best, best) == 0, MOE_ERR_UNSUPPORTED_SHAPE, "moe_down_proj: tile does not fit smem");
+  const int cpg = best / kColGroups;
+  const int ch = (cpg % 32 == 0) ? 32 : (cpg % 20 == 0) ? 20 : (cpg % 16 == 0) ? 16 : (cpg % 8 == 0) ? 8 : 4;
+  GemmShape g = {};
+  g.rows = T;
+  g.k = h;
+  g.m_tiles = m_tiles;
+  g.n_tiles = (d + best - 1) / best;
+  g.tile_n = best;
+  g.half_rows = best;
+  g.second_off = 0;
+  g.cn = best_cc.cn;
+  g.cm = best_cc.cm;
+  g.pair = pair ? 1 : 0;
+  if (forced) {   // validate a forced multicast shape the same way the heuristic would
+    const ClusterChoice ok = choose_cluster("MOE_K3_CLUSTER", m_tiles, g.n_tiles, best, best, h, 3.0 * best);
+    g.cn = ok.cn;
+    g.cm = ok.cm;
+  }
+  MOE_REQUIRE(finish_shape(g, kEpiWarps * kBiasSmemPerWarp) == 0, MOE_ERR_UNSUPPORTED_SHAPE,
+              "moe_down_proj: tile does not fit smem");
   CUtensorMap th, tw;
-  int rc = make_tmap_bf16_2d(&th, H, static_cast<uint64_t>(T), static_cast<uint64_t>(h), kBlockM, kBlockK);
+  int rc = make_tmap_bf16_2d(&th, H, static_cast<uint64_t>(T), static_cast<uint64_t>(h), static_cast<uint32_t>(g.a_box_rows), kBlockK);
   if (rc) return rc;
-  rc = make_tmap_bf16_2d(&tw, w2p, static_cast<uint64_t>(d), static_cast<uint64_t>(h), static_cast<uint32_t>(best), kBlockK);
+  rc = make_tmap_bf16_2d(&tw, w2p, static_cast<uint64_t>(d), static_cast<uint64_t>(h), static_cast<uint32_t>(g.b_box_rows), kBlockK);
   if (rc) return rc;
   DownArgs a;
   a.b2 = b2;
   a.Y = static_cast<__nv_bfloat16*>(Y);
   a.d = d;
-  const int total = g.m_tiles * g.n_tiles;
-  const int grid = total < sms ? total : sms;
-  const size_t smem = smem_bytes(g);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define MOE_LAUNCH_DOWN(CHV)                                          \
-  do {                                                                \
-    rc = ensure_smem(reinterpret_cast<const void*>(&down_proj_kernel<CHV>), smem);                    \
-    if (rc) return rc;                                                \
-    down_proj_kernel<CHV><<<grid, kNumThreads, smem, st>>>(th, tw, g, a); \
-  } while (0)
+#define MOE_LAUNCH_DOWN(CHV)                                                       \
+  rc = g.pair ? launch_clustered(down_proj_kernel<CHV, true>, g, st, th, tw, g, a)  \
+              : launch_clustered(down_proj_kernel<CHV, false>, g, st, th, tw, g, a)
   switch (ch) {
     case 32: MOE_LAUNCH_DOWN(32); break;
+    case 20: MOE_LAUNCH_DOWN(20); break;
     case 16: MOE_LAUNCH_DOWN(16); break;
-    default: MOE_LAUNCH_DOWN(8); break;
+    case 8: MOE_LAUNCH_DOWN(8); break;
+    default: MOE_LAUNCH_DOWN(4); break;
   }
 #undef MOE_LAUNCH_DOWN
+  if (rc) return rc;
   return check_launch("moe_down_proj");
 }
 

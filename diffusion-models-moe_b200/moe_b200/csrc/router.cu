@@ -345,9 +345,9 @@ int moe_router_topk(const float* scores, const uint32_t* removed_bits, int k, ui
 
 int moe_hist_accumulate(const int16_t* idx, long long n, int E, unsigned long long* hist, void* stream) {
   using namespace moe;
-  MOE_REQUIRE(idx != nullptr && hist != nullptr, MOE_ERR_INVALID_ARGUMENT, "moe_hist_accumulate: NULL pointer");
   MOE_REQUIRE(n >= 0 && E >= 1 && E <= 8192, MOE_ERR_INVALID_ARGUMENT, "moe_hist_accumulate: n=%lld E=%d", n, E);
   if (n == 0) return MOE_OK;
+  MOE_REQUIRE(idx != nullptr && hist != nullptr, MOE_ERR_INVALID_ARGUMENT, "moe_hist_accumulate: NULL pointer");
   const long long per_cta = 256LL * 8 * 8;  // 8 vector loads of 8 labels per thread
   long long ctas = (n + per_cta - 1) / per_cta;
   const long long max_ctas = static_cast<long long>(sm_count()) * 8;

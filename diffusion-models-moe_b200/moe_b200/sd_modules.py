@@ -56,9 +56,9 @@ except ImportError:
 class FeedForward(nn.Module):
     """upstream FeedForward(dim, mult=4, activation_fn='geglu'): net = [GEGLU, Dropout(0), Linear]."""
 
-    def __init__(self, dim: int, mult: int = 4):
+    def __init__(self, dim: int, mult: int = 4, inner_dim=None):
         super().__init__()
-        inner = dim * mult
+        inner = dim * mult if inner_dim is None else inner_dim
         self.net = nn.ModuleList([GEGLU(dim, inner), nn.Dropout(0.0), LoRACompatibleLinear(inner, dim)])
 
     def forward(self, hidden_states, scale: float = 1.0):

@@ -131,6 +131,12 @@ MOE_API int moe_mask_pack(const uint8_t* dense, long long n, uint32_t* bits, voi
 MOE_API int moe_mask_union(const uint32_t* a, const uint32_t* b, uint32_t* out, long long n_words, void* stream);
 MOE_API int moe_mask_weights(const void* w2, const uint32_t* bits, void* w2m, int d, int h, void* stream);
 
+/* Profiling hook: with the environment variable MOE_DEBUG_MODE bit 16 set, the GEMM kernels record
+ * per-CTA cycle counts of their producer / MMA-issue loops; this copies the first n counters
+ * (8 per CTA: empty-wait, TMA-issue, iterations, acc-wait, full-wait, MMA-issue, commit, -) to a HOST
+ * buffer.  Synchronises the device.  Not part of the hot path. */
+MOE_API int moe_debug_counters(unsigned long long* host_out, int n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,6 +18,12 @@ from gpu_util import DEV, rel_err, r16, OUT_REL_TOL, label_sets
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def _no_grad():
+    with torch.no_grad():   # the reference hooks run inside the pipeline's no_grad
+        yield
+
+
 def load(golden_dir, name):
     return np.load(os.path.join(golden_dir, name + ".npz"), allow_pickle=False)
 
@@ -29,7 +35,7 @@ def T(a):
 def make_ff(g, ratio=None, with_down=True):
     """FeedForward carrying the fixture weights (bf16, on the GPU), MoEfied through helper.modify_ffn."""
     h2, d = g["w1"].shape
-    ff = FeedForward(d)
+    ff = FeedForward(d, inner_dim=h2 // 2)
     with torch.no_grad():
         ff.net[0].proj.weight.copy_(T(g["w1"]))
         ff.net[0].proj.bias.copy_(T(g["b1"]))
