@@ -22,7 +22,9 @@ SIGNATURES = {
                              c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "moe_router_topk": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
-    "moe_down_proj": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "moe_down_proj": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, ctypes.c_size_t,
+                              c_void_p]),
+    "moe_down_proj_workspace_bytes": (ctypes.c_size_t, [c_int, c_int, c_int]),
     "moe_hist_accumulate": (c_int, [c_void_p, c_ll, c_int, c_void_p, c_void_p]),
     "moe_colmax_f32": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "moe_colmax_bf16": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
@@ -32,7 +34,7 @@ SIGNATURES = {
     "moe_debug_counters": (c_int, [c_void_p, c_int]),
 }
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 _lib = None
 
 

@@ -57,11 +57,29 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
   return MOE_OK;
 }
 
+int make_tmap_bf16_kblocks(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                           uint32_t box_kblocks) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(MOE_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || cols % 64 != 0)
+    return fail(MOE_ERR_INVALID_ARGUMENT, "k-block tensor map needs a 16-byte aligned base and cols %% 64 == 0 (cols=%llu)",
+                (unsigned long long)cols);
+  cuuint64_t gdim[3] = {64, rows, cols / 64};
+  cuuint64_t gstr[2] = {cols * 2, 128};
+  cuuint32_t box[3] = {64, box_rows, box_kblocks};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(MOE_ERR_CUDA, "cuTensorMapEncodeTiled(3d) failed with CUresult %d", (int)r);
+  return MOE_OK;
+}
+
 }  // namespace moe
 
 extern "C" {
 
-int moe_abi_version(void) { return 1; }
+int moe_abi_version(void) { return 2; }
 const char* moe_last_error(void) { return moe::last_error_buf(); }
 long long moe_launch_count(void) { return moe::g_launches.load(); }
 void moe_reset_launch_count(void) { moe::g_launches.store(0); }

@@ -70,12 +70,15 @@ struct GemmShape {
   int b_boxes;       // B boxes one CTA issues per stage
   int m_ctiles, n_ctiles;
   int extra_smem;    // bytes after the stage ring (epilogue staging)
+  int ks;            // 64-wide k-blocks per pipeline stage (one barrier round trip per ks k-blocks)
+  int split_k;       // K3: number of K slices per output tile (1 = no split)
+  int kb_per_slice;  // 64-wide k-blocks per slice (a multiple of ks unless it is the last slice)
   int pair;          // 1: cta_group::2 -- the two CTAs of a cluster pair share one 256 x tile_n UMMA
   int debug;         // MOE_DEBUG_MODE bits: 1 = no TMA loads, 2 = no MMAs, 4 = no epilogue math (profiling only)
 };
 
 // exact GELU x * Phi(x) with Phi from 0.5 * erfc(|x|/sqrt2) = 2^(P7(t)), t = min(|x|/sqrt2, 4.3):
-// branch-free, one MUFU.EX2 + 7 FFMA; max abs error 4e-7 on [-3, 3] (fp32 rounding level; the
+// branch-free, one MUFU.EX2 + 8 FFMA; max abs error 4e-7 on [-3, 3] (fp32 rounding level; the
 // libdevice erff path costs ~2x the instructions and diverges).  Coefficients: weighted minimax fit.
 __device__ __forceinline__ float gelu_erf(float x) {
   const float t = fminf(fabsf(x) * 0.70710678118654752f, 4.3f);
@@ -88,8 +91,8 @@ __device__ __forceinline__ float gelu_erf(float x) {
   q = fmaf(q, t, -1.6279140710830688f);
   q = fmaf(q, t, -0.9999999403953552f);
   const float e = tc::ex2_approx(q);               // 0.5 * erfc(t)
-  const float phi = x >= 0.f ? 1.0f - e : e;
-  return x * phi;
+  // x * Phi(x) with Phi = 1 - e (x >= 0) or e (x < 0)  ==  max(x, 0) - |x| * e
+  return fmaf(-fabsf(x), e, fmaxf(x, 0.f));
 }
 
 template <int ACT>
@@ -118,19 +121,37 @@ __device__ __forceinline__ void store_words(__nv_bfloat16* dst, const uint32_t* 
   }
 }
 
+// same, to a shared-memory address
+template <int kWords>
+__device__ __forceinline__ void store_words_smem(uint32_t addr, const uint32_t* w) {
+  if constexpr (kWords % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < kWords / 4; ++i) tc::sts_b32x4(addr + 16 * i, w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < kWords / 2; ++i) tc::sts_b32x2(addr + 8 * i, w[2 * i], w[2 * i + 1]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // Tile schedule: cluster c takes cluster tiles c, c + n_clusters, ...; inside a cluster tile the
 // CTA of rank (rn, rm) owns CTA tile (m = mct * cm + rm, n = nct * cn + rn).
 // ------------------------------------------------------------------------------------------
 struct TileCoord {
   int m_blk, n_blk;
+  int slice, kb_begin, kb_end;   // split-K: this work item's K slice, in 64-wide k-blocks
 };
 __device__ __forceinline__ bool tile_at(const GemmShape& g, int it, int rn, int rm, TileCoord& t) {
   const int csize = g.cn * g.cm;
-  const int ct = static_cast<int>(blockIdx.x) / csize + it * (static_cast<int>(gridDim.x) / csize);
-  if (ct >= g.m_ctiles * g.n_ctiles) return false;
+  int ct = static_cast<int>(blockIdx.x) / csize + it * (static_cast<int>(gridDim.x) / csize);
+  if (ct >= g.m_ctiles * g.n_ctiles * g.split_k) return false;
+  t.slice = ct % g.split_k;       // slices of one tile run side by side on different CTAs
+  ct /= g.split_k;
   t.m_blk = (ct / g.n_ctiles) * g.cm + rm;
   t.n_blk = (ct % g.n_ctiles) * g.cn + rn;
+  const int num_kb = (g.k + kBlockK - 1) / kBlockK;
+  t.kb_begin = t.slice * g.kb_per_slice;
+  t.kb_end = min(num_kb, t.kb_begin + g.kb_per_slice);
   return true;
 }
 
@@ -142,7 +163,6 @@ __device__ __forceinline__ bool tile_at(const GemmShape& g, int it, int rn, int 
 template <bool PAIR>
 __device__ __forceinline__ void producer_loop(const CUtensorMap* tmap_a, const CUtensorMap* tmap_b, uint8_t* smem,
                                               PipeBarriers* bars, const GemmShape& g, int rn, int rm, bool do_a) {
-  const int num_kb = (g.k + kBlockK - 1) / kBlockK;
   uint16_t row_mask = 0, col_mask = 0;   // CTAs sharing my A tile / my B tile
   for (int j = 0; j < g.cn; ++j) row_mask |= static_cast<uint16_t>(1u << (rm * g.cn + j));
   for (int i = 0; i < g.cm; ++i) col_mask |= static_cast<uint16_t>(1u << (i * g.cn + rn));
@@ -154,14 +174,14 @@ __device__ __forceinline__ void producer_loop(const CUtensorMap* tmap_a, const C
   const bool prof = (g.debug & 16) != 0 && do_a;
   long long c_wait = 0, c_issue = 0, n_iter = 0;
   for (int it = 0; tile_at(g, it, rn, rm, t); ++it) {
-    for (int kb = 0; kb < num_kb; ++kb) {
+    for (int kb = t.kb_begin; kb < t.kb_end; kb += g.ks) {
       const long long t0 = prof ? clock64() : 0;
       tc::mbar_wait(&bars->empty[s], ph ^ 1u);
       const long long t1 = prof ? clock64() : 0;
       c_wait += t1 - t0;
       ++n_iter;
       uint8_t* sa = smem + s * g.stage_bytes;
-      uint8_t* sb = sa + kABytes;
+      uint8_t* sb = sa + g.ks * kABytes;
       if (tc::elect_one()) {
       if (g.debug & 1) {   // profiling: pretend the stage arrived
         if (do_a && (!pair || rm == 0)) tc::mbar_arrive(&bars->full[s]);
@@ -170,12 +190,18 @@ __device__ __forceinline__ void producer_loop(const CUtensorMap* tmap_a, const C
         const uint32_t full_leader = tc::mapa_u32(&bars->full[s], 0);
         if (do_a) {
           if (rm == 0) tc::mbar_arrive_expect_tx(&bars->full[s], static_cast<uint32_t>(2 * g.stage_bytes));
-          tc::tma_load_2d_2sm(sa, tmap_a, full_leader, kb * kBlockK, t.m_blk * kBlockM);
+          if (g.ks > 1)
+            tc::tma_load_3d_2sm(sa, tmap_a, full_leader, 0, t.m_blk * kBlockM, kb);
+          else
+            tc::tma_load_2d_2sm(sa, tmap_a, full_leader, kb * kBlockK, t.m_blk * kBlockM);
         } else {
           const int j0 = rm * b_slice_rows;   // this CTA's half of the tile's weight rows
           const int grow = (j0 < g.half_rows) ? t.n_blk * g.half_rows + j0
                                               : g.second_off + t.n_blk * g.half_rows + (j0 - g.half_rows);
-          tc::tma_load_2d_2sm(sb, tmap_b, full_leader, kb * kBlockK, grow);
+          if (g.ks > 1)
+            tc::tma_load_3d_2sm(sb, tmap_b, full_leader, 0, grow, kb);
+          else
+            tc::tma_load_2d_2sm(sb, tmap_b, full_leader, kb * kBlockK, grow);
         }
       } else if (do_a) {
         // (non-pair) this CTA receives the whole stage (its own slices + its peers' multicasts)
@@ -183,6 +209,8 @@ __device__ __forceinline__ void producer_loop(const CUtensorMap* tmap_a, const C
         const int a_row0 = rn * g.a_box_rows;
         if (g.cn > 1)
           tc::tma_load_2d_mc(sa + a_row0 * 128, tmap_a, &bars->full[s], kb * kBlockK, t.m_blk * kBlockM + a_row0, row_mask);
+        else if (g.ks > 1)
+          tc::tma_load_3d(sa, tmap_a, &bars->full[s], 0, t.m_blk * kBlockM, kb);
         else
           tc::tma_load_2d(sa, tmap_a, &bars->full[s], kb * kBlockK, t.m_blk * kBlockM);
       } else {
@@ -192,6 +220,8 @@ __device__ __forceinline__ void producer_loop(const CUtensorMap* tmap_a, const C
                                               : g.second_off + t.n_blk * g.half_rows + (j0 - g.half_rows);
           if (g.cm > 1)
             tc::tma_load_2d_mc(sb + j0 * 128, tmap_b, &bars->full[s], kb * kBlockK, grow, col_mask);
+          else if (g.ks > 1)
+            tc::tma_load_3d(sb, tmap_b, &bars->full[s], 0, grow, kb);   // ks > 1 implies a single B box
           else
             tc::tma_load_2d(sb + j0 * 128, tmap_b, &bars->full[s], kb * kBlockK, grow);
         }
@@ -215,7 +245,6 @@ __device__ __forceinline__ void producer_loop(const CUtensorMap* tmap_a, const C
 template <bool PAIR>
 __device__ __forceinline__ void mma_loop(uint8_t* smem, PipeBarriers* bars, const GemmShape& g, uint32_t tmem_base,
                                          int rn, int rm) {
-  const int num_kb = (g.k + kBlockK - 1) / kBlockK;
   constexpr bool pair = PAIR;
   const uint32_t idesc = tc::umma_idesc_bf16_f32(pair ? 2 * kBlockM : kBlockM, static_cast<uint32_t>(g.tile_n));
   uint16_t sender_mask = 0;   // every CTA that writes into my smem: my cluster row and column
@@ -236,25 +265,32 @@ __device__ __forceinline__ void mma_loop(uint8_t* smem, PipeBarriers* bars, cons
     tc::fence_after_thread_sync();
     if (prof) c_acc += clock64() - ta;
     const uint32_t d_tmem = tmem_base + as * kAccStride;
-    for (int kb = 0; kb < num_kb; ++kb) {
+    for (int kb = t.kb_begin; kb < t.kb_end; kb += g.ks) {
       const long long t0 = prof ? clock64() : 0;
       tc::mbar_wait(&bars->full[s], ph);
       tc::fence_after_thread_sync();
       const long long t1 = prof ? clock64() : 0;
       c_full += t1 - t0;
-      const uint32_t a_addr = tc::smem_u32(smem + s * g.stage_bytes);
-      const uint32_t b_addr = a_addr + kABytes;
+      const uint32_t a_base = tc::smem_u32(smem + s * g.stage_bytes);
+      const uint32_t b_base = a_base + g.ks * kABytes;
+      const uint32_t b_sub_bytes = static_cast<uint32_t>((pair ? g.tile_n / 2 : g.tile_n) * 128);
+      const int n_sub = min(g.ks, t.kb_end - kb);   // a slice's last stage may be partly empty (zero-filled)
       const bool leader_lane = tc::elect_one();
       if (leader_lane) {
+        for (int sub = 0; sub < n_sub; ++sub) {
+          const uint32_t a_addr = a_base + sub * kABytes;
+          const uint32_t b_addr = b_base + sub * b_sub_bytes;
 #pragma unroll
-        for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-          if (g.debug & 2) break;   // profiling: no tensor work
-          const uint64_t da = tc::umma_desc_kmajor_sw128(a_addr + k * kUmmaK * 2);
-          const uint64_t db = tc::umma_desc_kmajor_sw128(b_addr + k * kUmmaK * 2);
-          if constexpr (pair)
-            tc::umma_bf16_ss_2sm(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-          else
-            tc::umma_bf16_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            if (g.debug & 2) break;   // profiling: no tensor work
+            const uint64_t da = tc::umma_desc_kmajor_sw128(a_addr + k * kUmmaK * 2);
+            const uint64_t db = tc::umma_desc_kmajor_sw128(b_addr + k * kUmmaK * 2);
+            const uint32_t acc = (kb > t.kb_begin || sub != 0 || k != 0) ? 1u : 0u;
+            if constexpr (pair)
+              tc::umma_bf16_ss_2sm(d_tmem, da, db, idesc, acc);
+            else
+              tc::umma_bf16_ss(d_tmem, da, db, idesc, acc);
+          }
         }
       }
       const long long t2 = prof ? clock64() : 0;
@@ -299,7 +335,9 @@ template <bool PAIR>
 __device__ __forceinline__ PipeBarriers* setup_pipeline(uint8_t*& smem, uint8_t*& extra, const GemmShape& g,
                                                         const CUtensorMap* ta, const CUtensorMap* tb) {
   extern __shared__ uint8_t smem_raw[];
-  smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  // 1024-byte alignment by POINTER arithmetic (an integer round-trip would lose the shared address space and
+  // turn every later access into a generic LD / ST)
+  smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   extra = smem + g.stages * g.stage_bytes;
   PipeBarriers* bars = reinterpret_cast<PipeBarriers*>(extra + g.extra_smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -365,21 +403,26 @@ struct GegluArgs {
   float* scores;                   // [T, E] or null
   __nv_bfloat16* gate_out;         // [T, h] or null       (FEAT path)
   int h, E, es, nv;                // nv = neuron pairs per tile (tile_n = 2 nv)
+  // host-precomputed so the epilogue never divides: experts per tile, chunks per expert inside a column
+  // group (0 if an expert spans groups), groups per expert (1 if experts fit a group)
+  int experts_per_tile, chunks_per_expert, span;
 };
 
 // One column group (cpg = nv / 4 neuron pairs) of one tile for the token row this thread owns.
-// CH divides both cpg and es, so a chunk never straddles an expert.
+// CH divides both cpg and es, so a chunk never straddles an expert.  `e_first` is the id of the first
+// expert this group touches.  sbias / hrow / spart are shared-space addresses.
 template <int CH, int ACT, bool FEAT>
 __device__ __forceinline__ void geglu_epilogue_group(const GegluArgs& a, uint32_t taddr, const float* sbias,
-                                                     __nv_bfloat16* hrow_smem, float* spart, int row, bool row_ok,
-                                                     int n_tile0, int col0, int cpg, int q_row) {
+                                                     __nv_bfloat16* hrow, float* spart, int row, bool row_ok, int n0,
+                                                     int col0, int cpg, int e_first, int cg, int q) {
   float score = 0.f;
+  int chunk_in_expert = 0, e = e_first;
+  float* score_row = a.scores != nullptr ? a.scores + static_cast<size_t>(row) * a.E : nullptr;
   for (int c = 0; c < cpg; c += CH) {
     uint32_t v[CH], g[CH];
     tc::tmem_ld_cols<CH>(taddr + col0 + c, v);
     tc::tmem_ld_cols<CH>(taddr + a.nv + col0 + c, g);
     tc::tmem_ld_wait();
-    const int n = n_tile0 + col0 + c;   // first packed neuron of this chunk
     uint32_t hw[CH / 2];
     uint32_t gw[FEAT ? CH / 2 : 1];
 #pragma unroll
@@ -394,7 +437,7 @@ __device__ __forceinline__ void geglu_epilogue_group(const GegluArgs& a, uint32_
       for (int j = 0; j < 4; ++j) {
         gg[j] = activate<ACT>(gg[j]);
         if constexpr (FEAT) {
-          if (a.neuron_override != nullptr && __ldg(a.neuron_override + n + i + j)) gg[j] = a.override_value;
+          if (a.neuron_override != nullptr && __ldg(a.neuron_override + n0 + c + i + j)) gg[j] = a.override_value;
         }
         score += gg[j];
       }
@@ -405,29 +448,28 @@ __device__ __forceinline__ void geglu_epilogue_group(const GegluArgs& a, uint32_
         gw[i / 2 + 1] = pack_bf16x2(gg[2], gg[3]);
       }
     }
-    store_words<CH / 2>(hrow_smem + col0 + c, hw);   // staged; one TMA store per tile writes it out
+    store_words<CH / 2>(hrow + col0 + c, hw);   // staged in smem; one TMA store per tile writes it out
     if constexpr (FEAT) {
-      if (a.gate_out != nullptr && row_ok) store_words<CH / 2>(a.gate_out + static_cast<size_t>(row) * a.h + n, gw);
+      if (a.gate_out != nullptr && row_ok)
+        store_words<CH / 2>(a.gate_out + static_cast<size_t>(row) * a.h + n0 + c, gw);
     }
-    // expert boundary inside the group (es < cpg): flush the finished expert's score
-    if (a.es < cpg && ((c + CH) % a.es) == 0) {
-      if (a.scores != nullptr && row_ok) a.scores[static_cast<size_t>(row) * a.E + (n + CH - a.es) / a.es] = score;
+    // experts that fit inside the group: flush a finished expert's score
+    if (a.chunks_per_expert > 0 && ++chunk_in_expert == a.chunks_per_expert) {
+      if (score_row != nullptr && row_ok) score_row[e] = score;
       score = 0.f;
+      chunk_in_expert = 0;
+      ++e;
     }
   }
-  if (a.es >= cpg && a.scores != nullptr) {
-    if (a.es == cpg) {
-      if (row_ok) a.scores[static_cast<size_t>(row) * a.E + (n_tile0 + col0) / a.es] = score;
-    } else {
-      // one expert spans `span` adjacent column groups: combine the partial sums through smem
-      const int span = a.es / cpg, cg = col0 / cpg;
-      spart[q_row * kColGroups + cg] = score;
-      tc::named_bar_sync(2 + (q_row >> 5), 4 * 32);   // the 4 warps of this lane quarter
-      if ((cg % span) == 0 && row_ok) {
-        float tot = 0.f;
-        for (int j = 0; j < span; ++j) tot += spart[q_row * kColGroups + cg + j];
-        a.scores[static_cast<size_t>(row) * a.E + (n_tile0 + col0) / a.es] = tot;
-      }
+  if (a.chunks_per_expert == 0 && a.scores != nullptr) {
+    // one expert spans `span` adjacent column groups: combine the partial sums through smem
+    volatile float* slot = spart + (32 * q + (threadIdx.x & 31)) * kColGroups;
+    slot[cg] = score;
+    tc::named_bar_sync(2 + q, 4 * 32);   // the 4 warps of this TMEM lane quarter
+    if ((cg % a.span) == 0 && row_ok) {
+      float tot = 0.f;
+      for (int j = 0; j < a.span; ++j) tot += slot[cg + j];
+      score_row[e_first] = tot;
     }
   }
 }
@@ -453,18 +495,20 @@ geglu_up_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     const int cg = ew >> 2;            // column group 0..3
     const int cpg = a.nv / kColGroups;
     // epilogue smem: [2][128][nv] bf16 H staging | per-warp bias | partial scores
-    __nv_bfloat16* hstage = reinterpret_cast<__nv_bfloat16*>(extra);
+    uint8_t* hstage = extra;
     float* sbias = reinterpret_cast<float*>(extra + 2 * kBlockM * a.nv * 2) + ew * (kBiasSmemPerWarp / 4);
     float* spart = reinterpret_cast<float*>(extra + 2 * kBlockM * a.nv * 2 + kEpiWarps * kBiasSmemPerWarp);
     const bool store_thread = (ew == 0 && lane == 0);
     if (store_thread) tc::prefetch_tensormap(&tmap_h);
     const int q_row = 32 * q + lane;
+    const int col0 = cg * cpg;
+    // first expert this column group touches inside a tile (no division in the loop below)
+    const int e_in_tile = a.chunks_per_expert > 0 ? cg * (cpg / a.es) : cg / a.span;
     TileCoord t;
     for (int it = 0; tile_at(g, it, rn, rm, t); ++it) {
       const int as = it & 1;
       const uint32_t aph = (it >> 1) & 1u;
       const int n_tile0 = t.n_blk * a.nv;
-      const int col0 = cg * cpg;
       stage_bias(sbias, a.b1 != nullptr ? a.b1 + n_tile0 + col0 : nullptr,
                  a.b1 != nullptr ? a.b1 + a.h + n_tile0 + col0 : nullptr, cpg, lane);
       tc::mbar_wait(&bars->tmem_full[as], aph);
@@ -472,14 +516,16 @@ geglu_up_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + as * kAccStride;
       const int row = t.m_blk * kBlockM + q_row;
       const bool row_ok = row < g.rows;
-      __nv_bfloat16* hbuf = hstage + (it & 1) * kBlockM * a.nv;
+      uint8_t* hbuf = hstage + (it & 1) * kBlockM * a.nv * 2;
+      __nv_bfloat16* hrow = reinterpret_cast<__nv_bfloat16*>(hbuf) + q_row * a.nv;
+      const int e_first = t.n_blk * a.experts_per_tile + e_in_tile;
       if (g.debug & 4) {
       } else if (act == MOE_ACT_GELU)
-        geglu_epilogue_group<CH, MOE_ACT_GELU, FEAT>(a, taddr, sbias, hbuf + q_row * a.nv, spart, row, row_ok, n_tile0,
-                                                     col0, cpg, q_row);
+        geglu_epilogue_group<CH, MOE_ACT_GELU, FEAT>(a, taddr, sbias, hrow, spart, row, row_ok, n_tile0 + col0,
+                                                     col0, cpg, e_first, cg, q);
       else
-        geglu_epilogue_group<CH, MOE_ACT_RELU, FEAT>(a, taddr, sbias, hbuf + q_row * a.nv, spart, row, row_ok, n_tile0,
-                                                     col0, cpg, q_row);
+        geglu_epilogue_group<CH, MOE_ACT_RELU, FEAT>(a, taddr, sbias, hrow, spart, row, row_ok, n_tile0 + col0,
+                                                     col0, cpg, e_first, cg, q);
       // accumulator stage drained -> MMA may overwrite it
       tc::fence_before_thread_sync();
       __syncwarp();
@@ -512,6 +558,8 @@ struct DownArgs {
   const float* b2;     // [d] or null
   __nv_bfloat16* Y;    // [T, d]
   int d;
+  float* ws_partial;   // split-K: [split_k][T][d] fp32 partial sums
+  int* ws_counters;    // split-K: one arrival counter per output tile (kept at zero between calls)
 };
 
 template <int CH, bool PAIR>
@@ -547,36 +595,105 @@ down_proj_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_consta
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + as * kAccStride + cg * cpg;
       const int row = t.m_blk * kBlockM + 32 * q + lane;
       const bool row_ok = row < g.rows;
-      for (int c = 0; c < cpg; c += CH) {
-        if (g.debug & 4) break;
-        uint32_t acc[CH];
-        tc::tmem_ld_cols<CH>(taddr + c, acc);
-        tc::tmem_ld_wait();
-        uint32_t yw[CH / 2];
+      if (g.split_k == 1) {
+        for (int c = 0; c < cpg; c += CH) {
+          if (g.debug & 4) break;
+          uint32_t acc[CH];
+          tc::tmem_ld_cols<CH>(taddr + c, acc);
+          tc::tmem_ld_wait();
+          uint32_t yw[CH / 2];
 #pragma unroll
-        for (int i = 0; i < CH; i += 4) {
-          const float4 b = *reinterpret_cast<const float4*>(sbias + c + i);
-          yw[i / 2] = pack_bf16x2(__uint_as_float(acc[i]) + b.x, __uint_as_float(acc[i + 1]) + b.y);
-          yw[i / 2 + 1] = pack_bf16x2(__uint_as_float(acc[i + 2]) + b.z, __uint_as_float(acc[i + 3]) + b.w);
-        }
-        if (row_ok) {
-          __nv_bfloat16* dst = a.Y + static_cast<size_t>(row) * a.d + n0 + c;
-          if (c + CH <= nvalid) {
-            store_words<CH / 2>(dst, yw);
-          } else {
+          for (int i = 0; i < CH; i += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(sbias + c + i);
+            yw[i / 2] = pack_bf16x2(__uint_as_float(acc[i]) + b.x, __uint_as_float(acc[i + 1]) + b.y);
+            yw[i / 2 + 1] = pack_bf16x2(__uint_as_float(acc[i + 2]) + b.z, __uint_as_float(acc[i + 3]) + b.w);
+          }
+          if (row_ok) {
+            __nv_bfloat16* dst = a.Y + static_cast<size_t>(row) * a.d + n0 + c;
+            if (c + CH <= nvalid) {
+              store_words<CH / 2>(dst, yw);
+            } else {
 #pragma unroll
-            for (int i = 0; i < CH / 2; ++i)
-              if (c + 2 * i < nvalid) *reinterpret_cast<uint32_t*>(dst + 2 * i) = yw[i];
+              for (int i = 0; i < CH / 2; ++i)
+                if (c + 2 * i < nvalid) *reinterpret_cast<uint32_t*>(dst + 2 * i) = yw[i];
+            }
           }
         }
-      }
-      tc::fence_before_thread_sync();
-      __syncwarp();
-      if (lane == 0) {
-        if constexpr (PAIR)
-          tc::mbar_arrive_cluster(tc::mapa_u32(&bars->tmem_empty[as], 0));   // the leader's MMA thread waits
-        else
-          tc::mbar_arrive(&bars->tmem_empty[as]);
+        tc::fence_before_thread_sync();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (PAIR)
+            tc::mbar_arrive_cluster(tc::mapa_u32(&bars->tmem_empty[as], 0));   // the leader's MMA thread waits
+          else
+            tc::mbar_arrive(&bars->tmem_empty[as]);
+        }
+      } else {
+        // ---- split-K: park this slice's fp32 partial tile, the last slice to arrive reduces
+        const size_t plane = static_cast<size_t>(g.rows) * a.d;
+        float* part = a.ws_partial + t.slice * plane + static_cast<size_t>(row) * a.d + n0;
+        for (int c = 0; c < cpg; c += CH) {
+          uint32_t acc[CH];
+          tc::tmem_ld_cols<CH>(taddr + c, acc);
+          tc::tmem_ld_wait();
+          if (row_ok) {
+#pragma unroll
+            for (int i = 0; i < CH; i += 4)
+              if (c + i < nvalid)   // d and the group widths are multiples of 4
+                __stcg(reinterpret_cast<float4*>(part + c + i),
+                       make_float4(__uint_as_float(acc[i]), __uint_as_float(acc[i + 1]), __uint_as_float(acc[i + 2]),
+                                   __uint_as_float(acc[i + 3])));
+          }
+        }
+        tc::fence_before_thread_sync();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (PAIR)
+            tc::mbar_arrive_cluster(tc::mapa_u32(&bars->tmem_empty[as], 0));
+          else
+            tc::mbar_arrive(&bars->tmem_empty[as]);
+        }
+        __threadfence();                                   // partial tile visible device-wide ...
+        tc::named_bar_sync(kEpiBarrierId, kEpiThreads);    // ... before the arrival is counted
+        int* flag = reinterpret_cast<int*>(extra + kEpiWarps * kBiasSmemPerWarp);
+        if (ew == 0 && lane == 0) {
+          int* counter = a.ws_counters + t.m_blk * g.n_tiles + t.n_blk;
+          const int prev = atomicAdd(counter, 1);
+          const int last = prev == g.split_k - 1;
+          if (last) *counter = 0;                          // leave the workspace clean for the next call
+          *flag = last;
+        }
+        tc::named_bar_sync(kEpiBarrierId, kEpiThreads);
+        if (*flag) {
+          __threadfence();
+          // coalesced reduction over the whole 128 x tile_n tile: 4 consecutive columns per thread, all
+          // slices' loads in flight at once, summed in slice order (deterministic)
+          const int et = (warp - kEpiWarp0) * 32 + lane;            // 0 .. 511
+          const int cols4 = g.tile_n >> 2;                           // float4 groups per tile row
+          const int tile_col0 = t.n_blk * g.tile_n;
+          const int tile_row0 = t.m_blk * kBlockM;
+          for (int e = et; e < kBlockM * cols4; e += kEpiThreads) {
+            const int r = e / cols4, c4 = (e - r * cols4) << 2;
+            const int grow = tile_row0 + r, gcol = tile_col0 + c4;
+            if (grow >= g.rows || gcol >= a.d) continue;
+            const float* src = a.ws_partial + static_cast<size_t>(grow) * a.d + gcol;
+            float4 p[8];
+#pragma unroll
+            for (int sl = 0; sl < 8; ++sl)
+              if (sl < g.split_k) p[sl] = __ldcg(reinterpret_cast<const float4*>(src + sl * plane));
+            float4 sum = a.b2 != nullptr ? __ldg(reinterpret_cast<const float4*>(a.b2 + gcol)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int sl = 0; sl < 8; ++sl)
+              if (sl < g.split_k) {
+                sum.x += p[sl].x;
+                sum.y += p[sl].y;
+                sum.z += p[sl].z;
+                sum.w += p[sl].w;
+              }
+            *reinterpret_cast<uint2*>(a.Y + static_cast<size_t>(grow) * a.d + gcol) =
+                make_uint2(pack_bf16x2(sum.x, sum.y), pack_bf16x2(sum.z, sum.w));
+          }
+        }
+        tc::named_bar_sync(kEpiBarrierId, kEpiThreads);    // flag may be rewritten by the next tile
       }
     }
   }
@@ -656,6 +773,21 @@ static bool pair_enabled() {
   return !(e && atoi(e) == 0);
 }
 
+// k-blocks per pipeline stage: the deepest of {4, 2, 1} that still leaves >= 3 stages in shared memory
+// (MOE_KS overrides).  Needs K % 64 == 0 (3-D k-block tensor maps) and a single B box per stage.
+static int pick_ks(int k, int num_kb_per_item, int b_rows_per_cta, int extra_smem, bool allowed) {
+  if (!allowed || k % kBlockK != 0) return 1;
+  int forced = 0;
+  if (const char* e = getenv("MOE_KS")) forced = atoi(e);
+  for (int ks = 4; ks >= 1; ks >>= 1) {
+    if (forced >= 1 && ks > forced) continue;
+    if (ks > 1 && num_kb_per_item < 2 * ks) continue;
+    const int stage = ks * (kABytes + b_rows_per_cta * 128);
+    if ((kSmemLimit - 1024 - extra_smem - static_cast<int>(sizeof(PipeBarriers))) / stage >= 3) return ks;
+  }
+  return 1;
+}
+
 static int debug_mode() {
   const char* e = getenv("MOE_DEBUG_MODE");
   return e ? atoi(e) : 0;
@@ -669,7 +801,8 @@ static int finish_shape(GemmShape& g, int extra_smem) {
   g.b_boxes = slice / g.b_box_rows;
   g.m_ctiles = (g.m_tiles + g.cm - 1) / g.cm;
   g.n_ctiles = g.n_tiles / g.cn;
-  g.stage_bytes = kABytes + (g.pair ? g.tile_n / 2 : g.tile_n) * 128;
+  if (g.ks < 1) g.ks = 1;
+  g.stage_bytes = g.ks * (kABytes + (g.pair ? g.tile_n / 2 : g.tile_n) * 128);
   g.extra_smem = extra_smem;
   int stages = (kSmemLimit - 1024 - extra_smem - static_cast<int>(sizeof(PipeBarriers))) / g.stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
@@ -706,7 +839,7 @@ static int launch_clustered(void (*kernel)(KArgs...), const GemmShape& g, cudaSt
   int rc = ensure_smem(reinterpret_cast<const void*>(kernel), smem);
   if (rc) return rc;
   const int csize = g.cn * g.cm;
-  const long long ctiles = static_cast<long long>(g.m_ctiles) * g.n_ctiles;
+  const long long ctiles = static_cast<long long>(g.m_ctiles) * g.n_ctiles * g.split_k;
   long long n_clusters = sm_count() / csize;
   if (n_clusters > ctiles) n_clusters = ctiles;
   cudaLaunchConfig_t cfg = {};
@@ -784,8 +917,11 @@ int moe_geglu_up(const void* x, const void* w1p, const float* b1p, const uint8_t
   g.tile_n = 2 * nv;
   g.half_rows = nv;
   g.second_off = h;
+  g.split_k = 1;
+  g.kb_per_slice = (d + kBlockK - 1) / kBlockK;
   ClusterChoice forced_cc;
-  if (g.m_tiles >= 2 && pair_enabled() && !env_cluster("MOE_K1_CLUSTER", forced_cc)) {
+  // (measured: with K = 320 the kernel is epilogue-bound and pairing only couples the two epilogues)
+  if (g.m_tiles >= 2 && d >= 512 && pair_enabled() && !env_cluster("MOE_K1_CLUSTER", forced_cc)) {
     // cta_group::2: CTA 0 of the pair stages the value rows, CTA 1 the gate rows of the tile's weights
     g.pair = 1;
     g.cn = 1;
@@ -797,11 +933,20 @@ int moe_geglu_up(const void* x, const void* w1p, const float* b1p, const uint8_t
     g.cm = cc.cm;
   }
   const int extra = 2 * kBlockM * nv * 2 + kEpiWarps * kBiasSmemPerWarp + kBlockM * kColGroups * 4;
+  g.ks = pick_ks(d, g.kb_per_slice, nv, extra, g.pair != 0);   // pair mode: one B box (value or gate rows) per CTA
   MOE_REQUIRE(finish_shape(g, extra) == 0, MOE_ERR_UNSUPPORTED_SHAPE, "moe_geglu_up: tile does not fit smem");
   CUtensorMap tx, tw, th;
-  int rc = make_tmap_bf16_2d(&tx, x, static_cast<uint64_t>(T), static_cast<uint64_t>(d), static_cast<uint32_t>(g.a_box_rows), kBlockK);
-  if (rc) return rc;
-  rc = make_tmap_bf16_2d(&tw, w1p, static_cast<uint64_t>(2) * h, static_cast<uint64_t>(d), static_cast<uint32_t>(g.b_box_rows), kBlockK);
+  int rc;
+  if (g.ks > 1) {
+    rc = make_tmap_bf16_kblocks(&tx, x, static_cast<uint64_t>(T), static_cast<uint64_t>(d), kBlockM, static_cast<uint32_t>(g.ks));
+    if (rc) return rc;
+    rc = make_tmap_bf16_kblocks(&tw, w1p, static_cast<uint64_t>(2) * h, static_cast<uint64_t>(d), static_cast<uint32_t>(g.b_box_rows),
+                                static_cast<uint32_t>(g.ks));
+  } else {
+    rc = make_tmap_bf16_2d(&tx, x, static_cast<uint64_t>(T), static_cast<uint64_t>(d), static_cast<uint32_t>(g.a_box_rows), kBlockK);
+    if (rc) return rc;
+    rc = make_tmap_bf16_2d(&tw, w1p, static_cast<uint64_t>(2) * h, static_cast<uint64_t>(d), static_cast<uint32_t>(g.b_box_rows), kBlockK);
+  }
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&th, H, static_cast<uint64_t>(T), static_cast<uint64_t>(h), kBlockM, static_cast<uint32_t>(nv), false);
   if (rc) return rc;
@@ -815,6 +960,9 @@ int moe_geglu_up(const void* x, const void* w1p, const float* b1p, const uint8_t
   a.E = E;
   a.es = es;
   a.nv = nv;
+  a.experts_per_tile = nv / es;
+  a.chunks_per_expert = (cpg % es == 0) ? es / ch : 0;
+  a.span = (cpg % es == 0) ? 1 : es / cpg;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool feat = neuron_override != nullptr || gate_out != nullptr;
 #define MOE_LAUNCH_GEGLU(CHV)                                                                              \
@@ -834,17 +982,32 @@ int moe_geglu_up(const void* x, const void* w1p, const float* b1p, const uint8_t
   return check_launch("moe_geglu_up");
 }
 
-int moe_down_proj(const void* H, const void* w2p, const float* b2, void* Y, int T, int h, int d, void* stream) {
+static const int kCounterBytes = 64 * 1024;   // head of the split-K workspace: per-tile arrival counters
+
+size_t moe_down_proj_workspace_bytes(int T, int h, int d) {
+  // enough for 8 K-slices of fp32 partial sums, capped at 64 MiB, plus the counters
+  (void)h;
+  size_t want = static_cast<size_t>(8) * static_cast<size_t>(T > 0 ? T : 0) * static_cast<size_t>(d > 0 ? d : 0) * 4;
+  const size_t cap = static_cast<size_t>(64) << 20;
+  if (want > cap) want = cap;
+  return kCounterBytes + want;
+}
+
+int moe_down_proj(const void* H, const void* w2p, const float* b2, void* Y, int T, int h, int d, void* workspace,
+                  size_t workspace_bytes, void* stream) {
   using namespace moe;
   MOE_REQUIRE(H && w2p && Y, MOE_ERR_INVALID_ARGUMENT, "moe_down_proj: NULL H / w2p / Y");
   MOE_REQUIRE(T >= 0 && h >= 8 && d >= 8, MOE_ERR_INVALID_ARGUMENT, "moe_down_proj: bad sizes T=%d h=%d d=%d", T, h, d);
   MOE_REQUIRE(h % 8 == 0 && d % 8 == 0, MOE_ERR_UNSUPPORTED_SHAPE, "moe_down_proj: h=%d and d=%d must be multiples of 8", h, d);
   MOE_REQUIRE((reinterpret_cast<uintptr_t>(Y) & 15) == 0, MOE_ERR_INVALID_ARGUMENT, "moe_down_proj: Y must be 16-byte aligned");
+  MOE_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, MOE_ERR_INVALID_ARGUMENT,
+              "moe_down_proj: workspace must be 16-byte aligned");
   if (T == 0) return MOE_OK;
-  // tile width: a multiple of 16, <= 256 (the last tile may overhang d by < 16 columns: TMA zero-fills
-  // the missing weight rows and the epilogue guards its stores).  Work units are CTA pairs (cta_group::2,
-  // 256 token rows) when there are at least two row tiles.  Per 16-wide K step the issuing thread needs
-  // ~90 cycles, the tensor pipe bn/2; among equal costs prefer more, narrower tiles (more SMs busy).
+  // Tile width bn (a multiple of 16, <= 256; the last tile may overhang d by < 16 columns: TMA zero-fills the
+  // missing weight rows and the epilogue guards its stores) and split-K factor S are chosen together.
+  // Work units are CTA pairs (cta_group::2, 256 token rows) when there are at least two row tiles.  The cost
+  // model (cycles) is fitted to profiles/r01_debug_clock*.log; every work item pays ~3000 for pipeline ramp +
+  // epilogue; split-K adds a reduction pass proportional to slices x tile width.
   const int m_tiles = (T + kBlockM - 1) / kBlockM;
   const int sms = sm_count();
   ClusterChoice forced_cc = {1, 1};
@@ -852,22 +1015,57 @@ int moe_down_proj(const void* H, const void* w2p, const float* b2, void* Y, int 
   const bool pair = m_tiles >= 2 && pair_enabled() && !forced;
   const int units = pair ? sms / 2 : sms;
   const int m_units = pair ? (m_tiles + 1) / 2 : m_tiles;
-  int best = 0;
+  const int num_kb = (h + kBlockK - 1) / kBlockK;
+  int max_split = 1;
+  if (workspace != nullptr && workspace_bytes > static_cast<size_t>(kCounterBytes) && !forced && d % 4 == 0) {
+    const size_t per_slice = static_cast<size_t>(T) * d * 4;
+    const size_t fit = (workspace_bytes - kCounterBytes) / per_slice;
+    max_split = fit > 8 ? 8 : static_cast<int>(fit);
+    if (const char* e = getenv("MOE_K3_SPLIT")) {
+      const int cap = atoi(e);
+      if (cap >= 1 && cap < max_split) max_split = cap;
+    }
+    if (max_split < 1) max_split = 1;
+  }
+  int best = 0, best_split = 1;
   double best_cost = 1e300;
   for (int bn = 256; bn >= 16; bn -= 16) {
     if (bn - (d % bn ? d % bn : bn) >= 16) continue;
     if (pair && (bn / 2) % 8) continue;                  // each CTA of a pair stages bn/2 weight rows
-    const long long tiles = static_cast<long long>(m_units) * ((d + bn - 1) / bn);
-    const long long rounds = (tiles + units - 1) / units;
-    const double per_kstep = bn / 2.0 > 90.0 ? bn / 2.0 : 90.0;
-    const double cost = rounds * ((h + kUmmaK - 1) / kUmmaK) * per_kstep + 2000.0 * rounds;   // + epilogue / ramp
-    if (cost < best_cost * 0.999) {
-      best_cost = cost;
+    const int n_tiles_c = (d + bn - 1) / bn;
+    if (static_cast<long long>(m_tiles + 1) * n_tiles_c * 4 > kCounterBytes) continue;
+    const long long tiles = static_cast<long long>(m_units) * n_tiles_c;
+    for (int sp = 1; sp <= max_split; ++sp) {
+      if (sp > 1 && num_kb / sp < 8) break;              // keep at least 8 k-blocks per slice
+      int kb_per = (num_kb + sp - 1) / sp;
+      const int ks_c = pick_ks(h, kb_per, pair ? bn / 2 : bn, kEpiWarps * kBiasSmemPerWarp + 16, !forced);
+      kb_per = (kb_per + ks_c - 1) / ks_c * ks_c;        // whole stages per slice
+      if (sp > 1 && (sp - 1) * kb_per >= num_kb) continue;   // no empty slices
+      const long long rounds = (tiles * sp + units - 1) / units;
+      // measured: ~230 cycles of barrier wait + commit per stage round, plus 4 MMAs per k-block at
+      // max(tensor, issue); the split-K epilogue (partials out, fence, reduction) is expensive
+      const double per_kblock = 230.0 / ks_c + (2.0 * bn > 220.0 ? 2.0 * bn : 220.0);
+      const double cost = rounds * (kb_per * per_kblock + 3000.0) + (sp > 1 ? 9000.0 + 40.0 * sp * bn : 0.0);
+      if (cost < best_cost * 0.999) {
+        best_cost = cost;
+        best = bn;
+        best_split = sp;
+      }
+    }
+  }
+  if (const char* e = getenv("MOE_K3_BN")) {   // tuning override: force the tile width (and MOE_K3_SPLIT the slices)
+    const int bn = atoi(e);
+    if (bn >= 16 && bn <= 256 && bn % 16 == 0 && (!pair || (bn / 2) % 8 == 0)) {
       best = bn;
+      best_split = max_split;
+      while (best_split > 1 && (best_split - 1) * ((num_kb + best_split - 1) / best_split) >= num_kb) --best_split;
     }
   }
   ClusterChoice best_cc = forced ? forced_cc : ClusterChoice{1, 1};
   if (pair) best_cc = ClusterChoice{1, 2};
+  if (getenv("MOE_DEBUG_PRINT"))
+    fprintf(stderr, "[moe_down_proj] T=%d h=%d d=%d -> bn=%d split<=%d pair=%d (model cost %.0f cycles)\n", T, h, d, best,
+            best_split, pair ? 1 : 0, best_cost);
   MOE_REQUIRE(best > 0, MOE_ERR_UNSUPPORTED_SHAPE, "moe_down_proj: no tile width for d=%d", d);
   const int cpg = best / kColGroups;
   const int ch = (cpg % 32 == 0) ? 32 : (cpg % 20 == 0) ? 20 : (cpg % 16 == 0) ? 16 : (cpg % 8 == 0) ? 8 : 4;
@@ -882,22 +1080,37 @@ int moe_down_proj(const void* H, const void* w2p, const float* b2, void* Y, int 
   g.cn = best_cc.cn;
   g.cm = best_cc.cm;
   g.pair = pair ? 1 : 0;
+  g.split_k = best_split;
+  g.kb_per_slice = (num_kb + best_split - 1) / best_split;
+  g.ks = pick_ks(h, g.kb_per_slice, pair ? best / 2 : best, kEpiWarps * kBiasSmemPerWarp + 16, !forced);
+  g.kb_per_slice = (g.kb_per_slice + g.ks - 1) / g.ks * g.ks;
+  while (g.split_k > 1 && (g.split_k - 1) * g.kb_per_slice >= num_kb) --g.split_k;
   if (forced) {   // validate a forced multicast shape the same way the heuristic would
     const ClusterChoice ok = choose_cluster("MOE_K3_CLUSTER", m_tiles, g.n_tiles, best, best, h, 3.0 * best);
     g.cn = ok.cn;
     g.cm = ok.cm;
   }
-  MOE_REQUIRE(finish_shape(g, kEpiWarps * kBiasSmemPerWarp) == 0, MOE_ERR_UNSUPPORTED_SHAPE,
+  MOE_REQUIRE(finish_shape(g, kEpiWarps * kBiasSmemPerWarp + 16) == 0, MOE_ERR_UNSUPPORTED_SHAPE,
               "moe_down_proj: tile does not fit smem");
   CUtensorMap th, tw;
-  int rc = make_tmap_bf16_2d(&th, H, static_cast<uint64_t>(T), static_cast<uint64_t>(h), static_cast<uint32_t>(g.a_box_rows), kBlockK);
-  if (rc) return rc;
-  rc = make_tmap_bf16_2d(&tw, w2p, static_cast<uint64_t>(d), static_cast<uint64_t>(h), static_cast<uint32_t>(g.b_box_rows), kBlockK);
+  int rc;
+  if (g.ks > 1) {
+    rc = make_tmap_bf16_kblocks(&th, H, static_cast<uint64_t>(T), static_cast<uint64_t>(h), kBlockM, static_cast<uint32_t>(g.ks));
+    if (rc) return rc;
+    rc = make_tmap_bf16_kblocks(&tw, w2p, static_cast<uint64_t>(d), static_cast<uint64_t>(h), static_cast<uint32_t>(g.b_box_rows),
+                                static_cast<uint32_t>(g.ks));
+  } else {
+    rc = make_tmap_bf16_2d(&th, H, static_cast<uint64_t>(T), static_cast<uint64_t>(h), static_cast<uint32_t>(g.a_box_rows), kBlockK);
+    if (rc) return rc;
+    rc = make_tmap_bf16_2d(&tw, w2p, static_cast<uint64_t>(d), static_cast<uint64_t>(h), static_cast<uint32_t>(g.b_box_rows), kBlockK);
+  }
   if (rc) return rc;
   DownArgs a;
   a.b2 = b2;
   a.Y = static_cast<__nv_bfloat16*>(Y);
   a.d = d;
+  a.ws_counters = static_cast<int*>(workspace);
+  a.ws_partial = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + kCounterBytes);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define MOE_LAUNCH_DOWN(CHV)                                                       \
   rc = g.pair ? launch_clustered(down_proj_kernel<CHV, true>, g, st, th, tw, g, a)  \

@@ -99,6 +99,22 @@ def router_topk(scores, k: int, *, removed_bits=None, want_bits: bool = True, wa
     return bits, idx
 
 
+_workspaces = {}
+
+
+def splitk_workspace(device, stream_ptr: int, nbytes: int) -> torch.Tensor:
+    """Zero-initialised split-K workspace, one per device, grown on demand (allocate it during warm-up,
+    before any CUDA-graph capture).  The kernel keeps its counter header at zero, so the buffer is
+    zero-filled only when (re)allocated.  Down-projections issued concurrently on several streams of
+    one device must not share it: serialise them or call the C ABI with per-stream workspaces."""
+    key = torch.device(device).index
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
 def down_proj(H, w2p, b2, out=None):
     """K3.  H bf16 [T, h]; w2p bf16 [d, h]; b2 f32 [d] or None -> Y bf16 [T, d]."""
     lib = _lib.load()
@@ -111,7 +127,9 @@ def down_proj(H, w2p, b2, out=None):
     Y = out if out is not None else torch.empty((T, d), dtype=torch.bfloat16, device=H.device)
     _need(Y, torch.bfloat16, "out", (T, d))
     with torch.cuda.device(H.device):
-        rc = lib.moe_down_proj(_ptr(H), _ptr(w2p), _ptr(b2), _ptr(Y), T, h, d, _stream(H))
+        st = _stream(H)
+        ws = splitk_workspace(H.device, st, int(lib.moe_down_proj_workspace_bytes(T, h, d)))
+        rc = lib.moe_down_proj(_ptr(H), _ptr(w2p), _ptr(b2), _ptr(Y), T, h, d, _ptr(ws), ws.numel(), st)
     _lib.check(rc, "moe_down_proj")
     return Y
 

@@ -21,6 +21,7 @@
 #ifndef MOE_B200_H
 #define MOE_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -102,9 +103,16 @@ MOE_API int moe_router_topk(const float* scores, const uint32_t* removed_bits, i
  * Replaces: upstream FeedForward.net[2] (Linear(h, d)) and
  * remove_wanda_neurons_fast.py:69-83 (F.linear(x, W2*(1-M), b2)).
  *   H bf16 [T, h]   w2p bf16 [d, h] (columns in packed order)   b2 f32 [d] or NULL   Y bf16 [T, d] out
+ * Small-T shapes split the K loop over several CTAs: fp32 partial tiles go to `workspace`, the last slice to
+ * arrive sums them in a fixed order (deterministic), adds b2 and writes Y.
  */
 MOE_API int moe_down_proj(const void* H, const void* w2p, const float* b2, void* Y, int T, int h, int d,
-                  void* stream);
+                  void* workspace, size_t workspace_bytes, void* stream);
+/* Recommended size of the optional split-K workspace of moe_down_proj (device memory, 16-byte aligned).
+ * Its first 64 KiB are per-tile arrival counters: the caller zero-fills the buffer ONCE after allocating it;
+ * the kernel leaves the counters at zero.  One workspace per concurrently running stream.  With
+ * workspace == NULL the kernel never splits K (slow for T <= 512 with h >= 2560). */
+MOE_API size_t moe_down_proj_workspace_bytes(int T, int h, int d);
 
 /*
  * K4 -- standalone expert-frequency histogram over stored labels:

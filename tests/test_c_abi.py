@@ -59,7 +59,7 @@ def test_argument_validation_without_gpu(lib):
     assert rc == -2 and b"multiples of 8" in lib.moe_last_error()
     rc = lib.moe_geglu_up(1, 1, None, None, 0.0, 16, None, None, 4, 32, 96, 16, 6, 0, None)
     assert rc == -2 and b"expert size" in lib.moe_last_error()
-    rc = lib.moe_mask_weights(16, 16, 16, 4, 48, None)
+    rc = lib.moe_mask_weights(16, 16, 16, 4, 48, None)  # h % 32
     assert rc == -2
 
 

@@ -145,7 +145,11 @@ def test_remove_experts_hook(lib, golden_dir, tmp_path):
         n = safe.shape[0]
         Hc = unpack_cols(H, mod).reshape(n, -1)
         assert rel_err(Hc[safe], orc[0].reshape(n, -1)[safe]) < OUT_REL_TOL
-        assert rel_err(Hc[safe], T(g[f"H_t{t}_l{l}"]).reshape(n, -1)[safe]) < 3e-2   # vs fp32-input reference
+        # vs the reference's own fp32-input output: tokens whose margin in the REFERENCE run is wide enough
+        # that bf16 input rounding cannot change the selected set
+        wide = (O.topk_margin(T(g[f"score_t{t}_l{l}"]), mod.k) > 0.25).numpy() if mod.k < pat.shape[0] else safe
+        assert wide.mean() > 0.3
+        assert rel_err(Hc[wide], T(g[f"H_t{t}_l{l}"]).reshape(n, -1)[wide]) < OUT_REL_TOL
         if lst and t < 20:
             assert torch.all(Hc[:, (pat[lst].sum(0) > 0)] == 0)
     rec.timestep, rec.layer = 0, 1
