@@ -366,6 +366,9 @@ __device__ __forceinline__ PipeBarriers* setup_pipeline(uint8_t*& smem, uint8_t*
   __syncthreads();
   if (g.cn * g.cm > 1) tc::cluster_sync_all();   // peers' barriers exist before anything is multicast
   tc::fence_after_thread_sync();
+  // everything above overlapped the previous kernel's tail (PDL); from here on we touch its outputs
+  pdl_wait();
+  if (threadIdx.x == 0) pdl_launch_dependents();
   return bars;
 }
 
@@ -502,6 +505,8 @@ geglu_up_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     if (store_thread) tc::prefetch_tensormap(&tmap_h);
     const int q_row = 32 * q + lane;
     const int col0 = cg * cpg;
+    const bool eprof = (g.debug & 16) != 0;
+    long long e_wait = 0, e_math = 0, e_store = 0, e_tiles = 0;
     // first expert this column group touches inside a tile (no division in the loop below)
     const int e_in_tile = a.chunks_per_expert > 0 ? cg * (cpg / a.es) : cg / a.span;
     TileCoord t;
@@ -511,8 +516,10 @@ geglu_up_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       const int n_tile0 = t.n_blk * a.nv;
       stage_bias(sbias, a.b1 != nullptr ? a.b1 + n_tile0 + col0 : nullptr,
                  a.b1 != nullptr ? a.b1 + a.h + n_tile0 + col0 : nullptr, cpg, lane);
+      const long long te0 = eprof ? clock64() : 0;
       tc::mbar_wait(&bars->tmem_full[as], aph);
       tc::fence_after_thread_sync();
+      const long long te1 = eprof ? clock64() : 0;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + as * kAccStride;
       const int row = t.m_blk * kBlockM + q_row;
       const bool row_ok = row < g.rows;
@@ -526,6 +533,7 @@ geglu_up_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       else
         geglu_epilogue_group<CH, MOE_ACT_RELU, FEAT>(a, taddr, sbias, hrow, spart, row, row_ok, n_tile0 + col0,
                                                      col0, cpg, e_first, cg, q);
+      const long long te2 = eprof ? clock64() : 0;
       // accumulator stage drained -> MMA may overwrite it
       tc::fence_before_thread_sync();
       __syncwarp();
@@ -545,8 +553,24 @@ geglu_up_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         tc::tma_store_2d(&tmap_h, hbuf, n_tile0, t.m_blk * kBlockM);   // rows beyond T are clipped
         tc::tma_store_commit();
       }
+      if (eprof) {
+        e_wait += te1 - te0;
+        e_math += te2 - te1;
+        e_store += clock64() - te2;
+        ++e_tiles;
+      }
     }
     if (store_thread) tc::tma_store_wait<0>();
+    if (eprof && store_thread && blockIdx.x < 256) {
+      g_dbg_counters[blockIdx.x * 8 + 7] = e_tiles;
+      // pack the three epilogue sums into the CTA's slots 0..2 of a second bank (offset 1024)
+      if (blockIdx.x < 128) {
+        g_dbg_counters[1024 + blockIdx.x * 8 + 0] = e_wait;
+        g_dbg_counters[1024 + blockIdx.x * 8 + 1] = e_math;
+        g_dbg_counters[1024 + blockIdx.x * 8 + 2] = e_store;
+        g_dbg_counters[1024 + blockIdx.x * 8 + 3] = e_tiles;
+      }
+    }
   }
   teardown_pipeline<PAIR>(bars, g);
 }
@@ -847,13 +871,15 @@ static int launch_clustered(void (*kernel)(KArgs...), const GemmShape& g, cudaSt
   cfg.blockDim = dim3(kNumThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = static_cast<unsigned>(csize);
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
   if (e != cudaSuccess) return fail(MOE_ERR_CUDA, "cudaLaunchKernelEx(cluster %dx%d): %s", g.cn, g.cm, cudaGetErrorString(e));
   return MOE_OK;
@@ -920,8 +946,9 @@ int moe_geglu_up(const void* x, const void* w1p, const float* b1p, const uint8_t
   g.split_k = 1;
   g.kb_per_slice = (d + kBlockK - 1) / kBlockK;
   ClusterChoice forced_cc;
-  // (measured: with K = 320 the kernel is epilogue-bound and pairing only couples the two epilogues)
-  if (g.m_tiles >= 2 && d >= 512 && pair_enabled() && !env_cluster("MOE_K1_CLUSTER", forced_cc)) {
+  int pair_min_d = 64;
+  if (const char* e = getenv("MOE_K1_PAIR_MIN_D")) pair_min_d = atoi(e);
+  if (g.m_tiles >= 2 && d >= pair_min_d && pair_enabled() && !env_cluster("MOE_K1_CLUSTER", forced_cc)) {
     // cta_group::2: CTA 0 of the pair stages the value rows, CTA 1 the gate rows of the tile's weights
     g.pair = 1;
     g.cn = 1;

@@ -7,6 +7,8 @@ namespace moe {
 // one thread -> one 32-bit word from 32 mask bytes
 __global__ void __launch_bounds__(256) mask_pack_kernel(const uint8_t* __restrict__ dense, long long n,
                                                         uint32_t* __restrict__ bits, long long n_words) {
+  pdl_wait();
+  pdl_launch_dependents();
   const long long w = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (w >= n_words) return;
   const long long base = w * 32;
@@ -29,6 +31,8 @@ __global__ void __launch_bounds__(256) mask_pack_kernel(const uint8_t* __restric
 
 __global__ void __launch_bounds__(256) mask_union_kernel(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b,
                                                          uint32_t* __restrict__ out, long long n_words, int vec_ok) {
+  pdl_wait();
+  pdl_launch_dependents();
   const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
   const long long nvec = vec_ok ? (n_words >> 2) : 0;
@@ -43,6 +47,8 @@ __global__ void __launch_bounds__(256) mask_union_kernel(const uint32_t* __restr
 // 8 bf16 (16 bytes) + one mask byte per thread
 __global__ void __launch_bounds__(256) mask_weights_kernel(const uint4* __restrict__ w, const uint8_t* __restrict__ bits,
                                                            uint4* __restrict__ out, long long n_vec) {
+  pdl_wait();
+  pdl_launch_dependents();
   const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = tid; i < n_vec; i += nthreads) {
@@ -76,7 +82,9 @@ int moe_mask_pack(const uint8_t* dense, long long n, uint32_t* bits, void* strea
   const long long n_words = (n + 31) / 32;
   const long long grid = (n_words + 255) / 256;
   MOE_REQUIRE(grid < (1LL << 31), MOE_ERR_UNSUPPORTED_SHAPE, "moe_mask_pack: mask too large");
-  mask_pack_kernel<<<static_cast<int>(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(dense, n, bits, n_words);
+  cudaError_t le = launch_pdl(mask_pack_kernel, dim3(static_cast<unsigned>(grid)), dim3(256), 0, static_cast<cudaStream_t>(stream),
+                              dense, n, bits, n_words);
+  if (le != cudaSuccess) return fail(MOE_ERR_CUDA, "moe_mask_pack launch: %s", cudaGetErrorString(le));
   return check_launch("moe_mask_pack");
 }
 
@@ -87,8 +95,9 @@ int moe_mask_union(const uint32_t* a, const uint32_t* b, uint32_t* out, long lon
   if (n_words == 0) return MOE_OK;
   const int vec_ok = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) |
                        reinterpret_cast<uintptr_t>(out)) & 15) == 0;
-  mask_union_kernel<<<stream_grid(n_words / 4 + 1, 256 * 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      a, b, out, n_words, vec_ok);
+  cudaError_t le = launch_pdl(mask_union_kernel, dim3(stream_grid(n_words / 4 + 1, 256 * 4)), dim3(256), 0,
+                              static_cast<cudaStream_t>(stream), a, b, out, n_words, vec_ok);
+  if (le != cudaSuccess) return fail(MOE_ERR_CUDA, "moe_mask_union launch: %s", cudaGetErrorString(le));
   return check_launch("moe_mask_union");
 }
 
@@ -100,8 +109,10 @@ int moe_mask_weights(const void* w2, const uint32_t* bits, void* w2m, int d, int
   MOE_REQUIRE(((reinterpret_cast<uintptr_t>(w2) | reinterpret_cast<uintptr_t>(w2m)) & 15) == 0,
               MOE_ERR_INVALID_ARGUMENT, "moe_mask_weights: weights must be 16-byte aligned");
   const long long n_vec = static_cast<long long>(d) * h / 8;
-  mask_weights_kernel<<<stream_grid(n_vec, 256 * 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const uint4*>(w2), reinterpret_cast<const uint8_t*>(bits), static_cast<uint4*>(w2m), n_vec);
+  cudaError_t le = launch_pdl(mask_weights_kernel, dim3(stream_grid(n_vec, 256 * 4)), dim3(256), 0,
+                              static_cast<cudaStream_t>(stream), static_cast<const uint4*>(w2),
+                              reinterpret_cast<const uint8_t*>(bits), static_cast<uint4*>(w2m), n_vec);
+  if (le != cudaSuccess) return fail(MOE_ERR_CUDA, "moe_mask_weights launch: %s", cudaGetErrorString(le));
   return check_launch("moe_mask_weights");
 }
 

@@ -54,6 +54,8 @@ __global__ void __launch_bounds__(kRouterWarps * 32) router_topk_kernel(const Ro
     removed[j] = (a.removed_bits != nullptr && lo < E) ? (__ldg(a.removed_bits + j) & valid[j]) : 0u;
   }
 
+  pdl_wait();                 // scores / H come from the previous kernel in the stream
+  pdl_launch_dependents();
   uint32_t cnt[SLOTS];
   float mx[SLOTS];
 #pragma unroll
@@ -231,6 +233,8 @@ __global__ void __launch_bounds__(256) hist_accumulate_kernel(const int16_t* __r
   extern __shared__ unsigned int bins[];
   for (int i = threadIdx.x; i < E; i += blockDim.x) bins[i] = 0u;
   __syncthreads();
+  pdl_wait();
+  pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
   const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
@@ -273,6 +277,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) colmax_kernel(const T* __restrict__ m, int rows, int cols,
                                                      float* __restrict__ out) {
   __shared__ float red[8][33];
+  pdl_wait();
+  pdl_launch_dependents();
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
   float mx = -INFINITY;
@@ -328,18 +334,20 @@ int moe_router_topk(const float* scores, const uint32_t* removed_bits, int k, ui
   const int grid = ctas_needed < max_ctas ? ctas_needed : max_ctas;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int slots = (E + 31) / 32;
+  cudaError_t le = cudaSuccess;
   if (slots <= 1)
-    router_topk_kernel<1><<<grid, kRouterWarps * 32, 0, st>>>(a);
+    le = launch_pdl(router_topk_kernel<1>, dim3(grid), dim3(kRouterWarps * 32), 0, st, a);
   else if (slots <= 2)
-    router_topk_kernel<2><<<grid, kRouterWarps * 32, 0, st>>>(a);
+    le = launch_pdl(router_topk_kernel<2>, dim3(grid), dim3(kRouterWarps * 32), 0, st, a);
   else if (slots <= 4)
-    router_topk_kernel<4><<<grid, kRouterWarps * 32, 0, st>>>(a);
+    le = launch_pdl(router_topk_kernel<4>, dim3(grid), dim3(kRouterWarps * 32), 0, st, a);
   else if (slots <= 8)
-    router_topk_kernel<8><<<grid, kRouterWarps * 32, 0, st>>>(a);
+    le = launch_pdl(router_topk_kernel<8>, dim3(grid), dim3(kRouterWarps * 32), 0, st, a);
   else if (slots <= 16)
-    router_topk_kernel<16><<<grid, kRouterWarps * 32, 0, st>>>(a);
+    le = launch_pdl(router_topk_kernel<16>, dim3(grid), dim3(kRouterWarps * 32), 0, st, a);
   else
-    router_topk_kernel<32><<<grid, kRouterWarps * 32, 0, st>>>(a);
+    le = launch_pdl(router_topk_kernel<32>, dim3(grid), dim3(kRouterWarps * 32), 0, st, a);
+  if (le != cudaSuccess) return fail(MOE_ERR_CUDA, "moe_router_topk launch: %s", cudaGetErrorString(le));
   return check_launch("moe_router_topk");
 }
 
@@ -352,8 +360,9 @@ int moe_hist_accumulate(const int16_t* idx, long long n, int E, unsigned long lo
   long long ctas = (n + per_cta - 1) / per_cta;
   const long long max_ctas = static_cast<long long>(sm_count()) * 8;
   if (ctas > max_ctas) ctas = max_ctas;
-  hist_accumulate_kernel<<<static_cast<int>(ctas), 256, E * sizeof(unsigned int), static_cast<cudaStream_t>(stream)>>>(
-      idx, n, E, hist);
+  cudaError_t le = launch_pdl(hist_accumulate_kernel, dim3(static_cast<unsigned>(ctas)), dim3(256), E * sizeof(unsigned int),
+                              static_cast<cudaStream_t>(stream), idx, n, E, hist);
+  if (le != cudaSuccess) return fail(MOE_ERR_CUDA, "moe_hist_accumulate launch: %s", cudaGetErrorString(le));
   return check_launch("moe_hist_accumulate");
 }
 
@@ -368,7 +377,8 @@ int moe_colmax_f32(const float* m, int T, int C, float* out, void* stream) {
   MOE_REQUIRE(m != nullptr && out != nullptr && T >= 0 && C >= 1, MOE_ERR_INVALID_ARGUMENT, "moe_colmax_f32: bad args");
   if (T == 0) return MOE_OK;
   dim3 grid((C + 31) / 32, colmax_grid_y(T));
-  colmax_kernel<float><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(m, T, C, out);
+  cudaError_t le = launch_pdl(colmax_kernel<float>, grid, dim3(256), 0, static_cast<cudaStream_t>(stream), m, T, C, out);
+  if (le != cudaSuccess) return fail(MOE_ERR_CUDA, "moe_colmax_f32 launch: %s", cudaGetErrorString(le));
   return check_launch("moe_colmax_f32");
 }
 
@@ -377,8 +387,9 @@ int moe_colmax_bf16(const void* m, int T, int C, float* out, void* stream) {
   MOE_REQUIRE(m != nullptr && out != nullptr && T >= 0 && C >= 1, MOE_ERR_INVALID_ARGUMENT, "moe_colmax_bf16: bad args");
   if (T == 0) return MOE_OK;
   dim3 grid((C + 31) / 32, colmax_grid_y(T));
-  colmax_kernel<__nv_bfloat16><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(m), T, C, out);
+  cudaError_t le = launch_pdl(colmax_kernel<__nv_bfloat16>, grid, dim3(256), 0, static_cast<cudaStream_t>(stream),
+                              static_cast<const __nv_bfloat16*>(m), T, C, out);
+  if (le != cudaSuccess) return fail(MOE_ERR_CUDA, "moe_colmax_bf16 launch: %s", cudaGetErrorString(le));
   return check_launch("moe_colmax_bf16");
 }
 
