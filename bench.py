@@ -46,7 +46,9 @@ def layer_list():
 
 
 def expert_size_for(mode, h):
-    return 20 if mode == "reference" else h // 20   # reference: 20 neurons/expert; literal: 20 experts
+    # reference: 20 neurons per expert (experiments/moefy_config.yaml:3 -> 64/128/256 experts);
+    # literal:   BASELINE.json config 1's geometry, 20 experts of 64 neurons at h=1280 -> 64-neuron experts
+    return 20 if mode == "reference" else 64
 
 
 def parse():
@@ -115,7 +117,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -239,6 +241,8 @@ def gpu_arm(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(50):          # keep the GPU under load while the first clock samples are taken
+        run_step()
     hist.zero_()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -250,28 +254,48 @@ def gpu_arm(args):
     ev1.record()
     barrier()
     ms_total = ev0.elapsed_time(ev1)
-    clocks = sampler.stop() if rank == 0 else None
     counts_ok = bool((hist[:, :].sum(1).cpu() == torch.tensor(
         [world * args.steps * L["s"] * L["k"] for L in layers])).all())
 
-    # ---- instrumented pass: per-launch CUDA events (same inputs, K steps) for the kernel breakdown
-    per_kernel = [0.0, 0.0, 0.0]
+    # ---- per-kernel breakdown: one CUDA graph per kernel type holding that kernel's 16 launches of a step,
+    # replayed back to back and timed with CUDA events on the launching stream (a per-launch event pair
+    # would time host launch gaps, not the kernels).  Buffers hold valid data from the runs above.
     k1_flops = sum(4.0 * L["d"] * L["h"] * L["T"] for L in layers)
     k3_flops = sum(2.0 * L["d"] * L["h"] * L["T"] for L in layers)
-    n_inst = min(args.steps, 20)
-    for _ in range(n_inst):
-        evs = {}
 
-        def record(li, slot):
-            e = torch.cuda.Event(enable_timing=True)
-            e.record()
-            evs[(li, slot)] = e
-        ffn_step(record)
+    def only(kind):
+        for li, L in enumerate(layers):
+            p = L["p"]
+            if kind == 0:
+                M.geglu_up(L["x"], p.w1p, p.b1p, L["E"], L["es"], M.ACT_GELU, out=L["H"], scores_out=L["scores"])
+            elif kind == 1:
+                M.router_topk(L["scores"], L["k"], want_bits=False, hist=hist[li, :L["E"]], H=L["H"],
+                              expert_size=L["es"], count_rows=(0, L["s"]))
+            else:
+                M.down_proj(L["H"], p.w2p, p.b2, out=L["y"])
+
+    per_kernel = []
+    n_inst = max(5, min(args.steps, 20))
+    for kind in range(3):
+        gk = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            only(kind)
+            torch.cuda.synchronize()
+            with torch.cuda.graph(gk, stream=side):
+                only(kind)
+        torch.cuda.current_stream().wait_stream(side)
+        for _ in range(3):
+            gk.replay()
         torch.cuda.synchronize()
-        for li in range(len(layers)):
-            for kk in range(3):
-                per_kernel[kk] += evs[(li, kk)].elapsed_time(evs[(li, kk + 1)])
-    per_kernel = [t / n_inst for t in per_kernel]           # ms per step spent in K1 / K2 / K3
+        k0, k1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        for _ in range(n_inst):
+            gk.replay()
+        k1e.record()
+        torch.cuda.synchronize()
+        per_kernel.append(k0.elapsed_time(k1e) / n_inst)    # ms per step spent in K1 / K2 / K3
 
     # ---- e2e: host buffers through the C-ABI triple, H2D + D2H inside the timed region
     h2d = sum(L["x_host"].numel() * 2 for L in layers)
@@ -297,6 +321,7 @@ def gpu_arm(args):
     barrier()
     ms_e2e = e0.elapsed_time(e1) / n_e2e
 
+    clocks = sampler.stop() if rank == 0 else None   # sampled across the timed region, the breakdown and e2e
     stats = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
@@ -320,7 +345,8 @@ def gpu_arm(args):
     k3_tf = k3_flops / (per_kernel[2] * 1e-3) / 1e12
     roofline = dict(bound="tensor", kernel="geglu_up_kernel (K1)", achieved=round(k1_tf, 2), peak=peak_tf,
                     unit="TFLOP/s", frac=round(k1_tf / peak_tf, 4), traffic=None, peak_source=peak_src,
-                    algorithmic="4*d*h FLOP per token, summed over the 16 launches of a step / summed launch time",
+                    algorithmic="4*d*h FLOP per token, summed over the 16 K1 launches of a step / their summed "
+                                "duration (CUDA events around a graph of exactly those launches)",
                     kernel_ms_per_step=dict(K1_geglu_up=round(per_kernel[0], 4), K2_router=round(per_kernel[1], 4),
                                             K3_down_proj=round(per_kernel[2], 4)),
                     K3_down_proj_tflops=round(k3_tf, 2), K3_frac=round(k3_tf / peak_tf, 4))
