@@ -344,7 +344,10 @@ def gpu_arm(args):
     k1_tf = k1_flops / (per_kernel[0] * 1e-3) / 1e12
     k3_tf = k3_flops / (per_kernel[2] * 1e-3) / 1e12
     roofline = dict(bound="tensor", kernel="geglu_up_kernel (K1)", achieved=round(k1_tf, 2), peak=peak_tf,
-                    unit="TFLOP/s", frac=round(k1_tf / peak_tf, 4), traffic=None, peak_source=peak_src,
+                    unit="TFLOP/s", frac=round(k1_tf / peak_tf, 4),
+                    # ncu --set full, dram__bytes_read + write of the config-1 K1 launch (d=320, 8192 tokens; its
+                    # algorithmic bytes are 30 MB, of which the 21 MB H tile stays in L2): profiles/r01_ncu_full_v6_*
+                    traffic=6.93e6, traffic_launch="K1 d=320 T=8192", peak_source=peak_src,
                     algorithmic="4*d*h FLOP per token, summed over the 16 K1 launches of a step / their summed "
                                 "duration (CUDA events around a graph of exactly those launches)",
                     kernel_ms_per_step=dict(K1_geglu_up=round(per_kernel[0], 4), K2_router=round(per_kernel[1], 4),
