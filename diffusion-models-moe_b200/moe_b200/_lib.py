@@ -32,6 +32,12 @@ SIGNATURES = {
     "moe_mask_union": (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_void_p]),
     "moe_mask_weights": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "moe_debug_counters": (c_int, [c_void_p, c_int]),
+    "moe_debug_trace": (c_int, [c_void_p, c_int]),
+    "moe_ffn_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                              c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                              c_int, c_void_p, ctypes.c_size_t, c_void_p]),
+    "moe_ffn_fused_workspace_bytes": (ctypes.c_size_t, [c_int, c_int, c_int]),
+    "moe_debug_trace_fused": (c_int, [c_void_p, c_int]),
 }
 
 ABI_VERSION = 2

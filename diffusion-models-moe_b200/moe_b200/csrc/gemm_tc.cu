@@ -47,6 +47,8 @@ constexpr int kEpiBarrierId = 1;
 
 // profiling counters (MOE_DEBUG_MODE bit 16): per CTA, cycles the producer / MMA threads spend per step
 __device__ unsigned long long g_dbg_counters[256 * 8];
+// timeline trace (MOE_DEBUG_MODE bit 32): per CTA, 64 globaltimer stamps (ns) at fixed points of the kernel
+__device__ unsigned long long g_trace[256 * 64];
 
 struct PipeBarriers {
   uint64_t full[kMaxStages];
@@ -76,6 +78,10 @@ struct GemmShape {
   int pair;          // 1: cta_group::2 -- the two CTAs of a cluster pair share one 256 x tile_n UMMA
   int debug;         // MOE_DEBUG_MODE bits: 1 = no TMA loads, 2 = no MMAs, 4 = no epilogue math (profiling only)
 };
+
+__device__ __forceinline__ void trace_at(const GemmShape& g, int slot) {
+  if ((g.debug & 32) && blockIdx.x < 256 && slot < 64) g_trace[blockIdx.x * 64 + slot] = tc::global_timer_ns();
+}
 
 // exact GELU x * Phi(x) with Phi from 0.5 * erfc(|x|/sqrt2) = 2^(P7(t)), t = min(|x|/sqrt2, 4.3):
 // branch-free, one MUFU.EX2 + 8 FFMA; max abs error 4e-7 on [-3, 3] (fp32 rounding level; the
@@ -173,10 +179,12 @@ __device__ __forceinline__ void producer_loop(const CUtensorMap* tmap_a, const C
   TileCoord t;
   const bool prof = (g.debug & 16) != 0 && do_a;
   long long c_wait = 0, c_issue = 0, n_iter = 0;
+  if (do_a && (threadIdx.x & 31) == 0) trace_at(g, 60);
   for (int it = 0; tile_at(g, it, rn, rm, t); ++it) {
     for (int kb = t.kb_begin; kb < t.kb_end; kb += g.ks) {
       const long long t0 = prof ? clock64() : 0;
       tc::mbar_wait(&bars->empty[s], ph ^ 1u);
+      if (do_a && (threadIdx.x & 31) == 0 && it == 0 && kb == t.kb_begin) trace_at(g, 61);
       const long long t1 = prof ? clock64() : 0;
       c_wait += t1 - t0;
       ++n_iter;
@@ -189,6 +197,7 @@ __device__ __forceinline__ void producer_loop(const CUtensorMap* tmap_a, const C
         // the leader's barrier collects the bytes of both CTAs of the pair
         const uint32_t full_leader = tc::mapa_u32(&bars->full[s], 0);
         if (do_a) {
+          if (it == 0 && kb == t.kb_begin) trace_at(g, 62);
           if (rm == 0) tc::mbar_arrive_expect_tx(&bars->full[s], static_cast<uint32_t>(2 * g.stage_bytes));
           if (g.ks > 1)
             tc::tma_load_3d_2sm(sa, tmap_a, full_leader, 0, t.m_blk * kBlockM, kb);
@@ -226,6 +235,7 @@ __device__ __forceinline__ void producer_loop(const CUtensorMap* tmap_a, const C
             tc::tma_load_2d(sb + j0 * 128, tmap_b, &bars->full[s], kb * kBlockK, grow);
         }
       }
+      if (do_a && it == 0 && kb == t.kb_begin) trace_at(g, 7);
       }
       __syncwarp();
       if (prof) c_issue += clock64() - t1;
@@ -277,6 +287,7 @@ __device__ __forceinline__ void mma_loop(uint8_t* smem, PipeBarriers* bars, cons
       const int n_sub = min(g.ks, t.kb_end - kb);   // a slice's last stage may be partly empty (zero-filled)
       const bool leader_lane = tc::elect_one();
       if (leader_lane) {
+        if (it == 0 && kb == t.kb_begin) trace_at(g, 3);
         for (int sub = 0; sub < n_sub; ++sub) {
           const uint32_t a_addr = a_base + sub * kABytes;
           const uint32_t b_addr = b_base + sub * b_sub_bytes;
@@ -320,6 +331,7 @@ __device__ __forceinline__ void mma_loop(uint8_t* smem, PipeBarriers* bars, cons
         tc::umma_commit_2sm_mc(&bars->tmem_full[as], 0x3);   // accumulator complete -> both epilogues
       else
         tc::umma_commit(&bars->tmem_full[as]);               // accumulator complete -> epilogue
+      trace_at(g, 8 + 4 * it);
     }
     __syncwarp();
   }
@@ -337,6 +349,7 @@ __device__ __forceinline__ PipeBarriers* setup_pipeline(uint8_t*& smem, uint8_t*
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment by POINTER arithmetic (an integer round-trip would lose the shared address space and
   // turn every later access into a generic LD / ST)
+  if (threadIdx.x == 0) trace_at(g, 0);
   smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   extra = smem + g.stages * g.stage_bytes;
   PipeBarriers* bars = reinterpret_cast<PipeBarriers*>(extra + g.extra_smem);
@@ -367,8 +380,10 @@ __device__ __forceinline__ PipeBarriers* setup_pipeline(uint8_t*& smem, uint8_t*
   if (g.cn * g.cm > 1) tc::cluster_sync_all();   // peers' barriers exist before anything is multicast
   tc::fence_after_thread_sync();
   // everything above overlapped the previous kernel's tail (PDL); from here on we touch its outputs
+  if (threadIdx.x == 0) trace_at(g, 1);
   pdl_wait();
   if (threadIdx.x == 0) pdl_launch_dependents();
+  if (threadIdx.x == 0) trace_at(g, 2);
   return bars;
 }
 
@@ -376,8 +391,10 @@ template <bool PAIR>
 __device__ __forceinline__ void teardown_pipeline(PipeBarriers* bars, const GemmShape& g) {
   tc::fence_before_thread_sync();
   __syncthreads();
+  if (threadIdx.x == 0) trace_at(g, 5);
   if (g.cn * g.cm > 1) tc::cluster_sync_all();   // nobody exits while a peer may still signal its smem
   tc::fence_after_thread_sync();
+  if (threadIdx.x == 0) trace_at(g, 6);
   if ((threadIdx.x >> 5) == 2) {
     if constexpr (PAIR)
       tc::tmem_dealloc_2sm<kTmemCols>(bars->tmem_base);
@@ -520,6 +537,7 @@ geglu_up_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       tc::mbar_wait(&bars->tmem_full[as], aph);
       tc::fence_after_thread_sync();
       const long long te1 = eprof ? clock64() : 0;
+      if (store_thread) trace_at(g, 8 + 4 * it + 1);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + as * kAccStride;
       const int row = t.m_blk * kBlockM + q_row;
       const bool row_ok = row < g.rows;
@@ -534,6 +552,7 @@ geglu_up_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         geglu_epilogue_group<CH, MOE_ACT_RELU, FEAT>(a, taddr, sbias, hrow, spart, row, row_ok, n_tile0 + col0,
                                                      col0, cpg, e_first, cg, q);
       const long long te2 = eprof ? clock64() : 0;
+      if (store_thread) trace_at(g, 8 + 4 * it + 2);
       // accumulator stage drained -> MMA may overwrite it
       tc::fence_before_thread_sync();
       __syncwarp();
@@ -552,6 +571,7 @@ geglu_up_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       if (store_thread) {
         tc::tma_store_2d(&tmap_h, hbuf, n_tile0, t.m_blk * kBlockM);   // rows beyond T are clipped
         tc::tma_store_commit();
+        trace_at(g, 8 + 4 * it + 3);
       }
       if (eprof) {
         e_wait += te1 - te0;
@@ -561,6 +581,7 @@ geglu_up_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       }
     }
     if (store_thread) tc::tma_store_wait<0>();
+    if (store_thread) trace_at(g, 4);
     if (eprof && store_thread && blockIdx.x < 256) {
       g_dbg_counters[blockIdx.x * 8 + 7] = e_tiles;
       // pack the three epilogue sums into the CTA's slots 0..2 of a second bank (offset 1024)
@@ -616,6 +637,7 @@ down_proj_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_consta
       stage_bias(sbias, a.b2 != nullptr ? a.b2 + n0 : nullptr, nullptr, nvalid, lane);
       tc::mbar_wait(&bars->tmem_full[as], aph);
       tc::fence_after_thread_sync();
+      if (ew == 0 && lane == 0) trace_at(g, 8 + 4 * it + 1);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + as * kAccStride + cg * cpg;
       const int row = t.m_blk * kBlockM + 32 * q + lane;
       const bool row_ok = row < g.rows;
@@ -719,7 +741,9 @@ down_proj_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_consta
         }
         tc::named_bar_sync(kEpiBarrierId, kEpiThreads);    // flag may be rewritten by the next tile
       }
+      if (ew == 0 && lane == 0) trace_at(g, 8 + 4 * it + 2);
     }
+    if (ew == 0 && lane == 0) trace_at(g, 4);
   }
   teardown_pipeline<PAIR>(bars, g);
 }
@@ -894,6 +918,16 @@ int moe_debug_counters(unsigned long long* host_out, int n) {
   MOE_REQUIRE(host_out != nullptr && n >= 0 && n <= 256 * 8, MOE_ERR_INVALID_ARGUMENT, "moe_debug_counters: bad args");
   cudaError_t e = cudaMemcpyFromSymbol(host_out, g_dbg_counters, sizeof(unsigned long long) * n);
   if (e != cudaSuccess) return fail(MOE_ERR_CUDA, "moe_debug_counters: %s", cudaGetErrorString(e));
+  return MOE_OK;
+}
+
+int moe_debug_trace(unsigned long long* host_out, int n) {
+  using namespace moe;
+  MOE_REQUIRE(host_out != nullptr && n >= 0 && n <= 256 * 64, MOE_ERR_INVALID_ARGUMENT, "moe_debug_trace: bad args");
+  cudaError_t e = cudaMemcpyFromSymbol(host_out, g_trace, sizeof(unsigned long long) * n);
+  if (e != cudaSuccess) return fail(MOE_ERR_CUDA, "moe_debug_trace: %s", cudaGetErrorString(e));
+  void* sym = nullptr;   // clear, so that the next traced launch is seen alone
+  if (cudaGetSymbolAddress(&sym, g_trace) == cudaSuccess) cudaMemset(sym, 0, sizeof(unsigned long long) * 256 * 64);
   return MOE_OK;
 }
 

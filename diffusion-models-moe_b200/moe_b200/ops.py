@@ -134,6 +134,63 @@ def down_proj(H, w2p, b2, out=None):
     return Y
 
 
+_fused_workspaces = {}
+
+
+def fused_workspace(device, nbytes: int) -> torch.Tensor:
+    """Zero-initialised workspace of the fused layer kernel (sync counters + split-K partials), one per device,
+    grown on demand; the kernel leaves its counters at zero (allocate during warm-up, before graph capture)."""
+    key = torch.device(device).index
+    ws = _fused_workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+        _fused_workspaces[key] = ws
+    return ws
+
+
+def ffn_fused(x, w1p, b1p, w2p, b2, n_experts: int, expert_size: int, k: int, act: int = ACT_GELU, *,
+              removed_bits=None, want_bits: bool = False, want_idx: bool = False, hist=None, count_rows=(0, 0),
+              mask_h: bool = True, H_out=None, scores_out=None, out=None, bits_out=None):
+    """One hooked layer call in one launch: K1 -> routing -> K3 (moe_ffn_fused).
+    Returns (Y bf16 [T, d], H bf16 [T, h] masked, scores f32 [T, E], active_bits | None, idx | None)."""
+    lib = _lib.load()
+    T, d = x.shape
+    h = w1p.shape[0] // 2
+    E = n_experts
+    W = (E + 31) // 32
+    dev = x.device
+    _need(x, torch.bfloat16, "x")
+    _need(w1p, torch.bfloat16, "w1p", (2 * h, d))
+    _need(w2p, torch.bfloat16, "w2p", (d, h))
+    if b1p is not None:
+        _need(b1p, torch.float32, "b1p", (2 * h,))
+    if b2 is not None:
+        _need(b2, torch.float32, "b2", (d,))
+    if removed_bits is not None:
+        _need(removed_bits, torch.int32, "removed_bits", (W,))
+    H = H_out if H_out is not None else torch.empty((T, h), dtype=torch.bfloat16, device=dev)
+    _need(H, torch.bfloat16, "H_out", (T, h))
+    scores = scores_out if scores_out is not None else torch.empty((T, E), dtype=torch.float32, device=dev)
+    _need(scores, torch.float32, "scores_out", (T, E))
+    Y = out if out is not None else torch.empty((T, d), dtype=torch.bfloat16, device=dev)
+    _need(Y, torch.bfloat16, "out", (T, d))
+    bits = None
+    if want_bits:
+        bits = bits_out if bits_out is not None else torch.empty((T, W), dtype=torch.int32, device=dev)
+        _need(bits, torch.int32, "bits_out", (T, W))
+    idx = torch.empty((T, k), dtype=torch.int16, device=dev) if want_idx else None
+    if hist is not None:
+        _need(hist, torch.int64, "hist", (E,))
+    with torch.cuda.device(dev):
+        ws = fused_workspace(dev, int(lib.moe_ffn_fused_workspace_bytes(T, d, h)))
+        rc = lib.moe_ffn_fused(_ptr(x), _ptr(w1p), _ptr(b1p), _ptr(w2p), _ptr(b2), _ptr(H), _ptr(scores), _ptr(Y),
+                               _ptr(removed_bits), int(k), _ptr(bits), _ptr(idx), _ptr(hist), int(count_rows[0]),
+                               int(count_rows[1]), T, d, h, E, int(expert_size), int(act), 1 if mask_h else 0, _ptr(ws),
+                               ws.numel(), _stream(x))
+    _lib.check(rc, "moe_ffn_fused")
+    return Y, H, scores, bits, idx
+
+
 def hist_accumulate(idx, n_experts: int, hist=None):
     """K4.  idx int16 (any shape) -> hist int64 [E] (accumulated in place if given)."""
     lib = _lib.load()

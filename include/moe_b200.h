@@ -139,11 +139,44 @@ MOE_API int moe_mask_pack(const uint8_t* dense, long long n, uint32_t* bits, voi
 MOE_API int moe_mask_union(const uint32_t* a, const uint32_t* b, uint32_t* out, long long n_words, void* stream);
 MOE_API int moe_mask_weights(const void* w2, const uint32_t* bits, void* w2m, int d, int h, void* stream);
 
+/*
+ * Fused layer call -- the whole MoEfied GEGLU FFN of one BasicTransformerBlock in ONE persistent kernel:
+ * up-projection + activation + product + expert scores (as moe_geglu_up), per-token top-k routing with the
+ * removed-expert rule, histogram and write-only masking of H (as moe_router_topk), down-projection (as
+ * moe_down_proj).  CTA pairs pass row blocks from phase to phase through counters in `workspace`, so the three
+ * stages overlap and the layer pays one launch ramp instead of three.
+ *
+ * Replaces, for one hooked layer call: moefy.py:10-27 / remove_skilled_experts.py:29-49 /
+ * frequency_measure.py:40-64 (hook body) followed by the stock ff.net.2 Linear [upstream].
+ *
+ *   x bf16 [T, d]   w1p bf16 [2h, d]   b1p f32 [2h] or NULL   w2p bf16 [d, h]   b2 f32 [d] or NULL
+ *   H bf16 [T, h] out (masked hidden state)   scores f32 [T, E] out   Y bf16 [T, d] out
+ *   removed_bits / k / active_bits / idx / hist / count_begin / count_end: as moe_router_topk
+ *   act: MOE_ACT_GELU | MOE_ACT_RELU     mask_h: 0 = leave H unmasked (routing outputs only)
+ *   workspace: device memory of moe_ffn_fused_workspace_bytes() bytes, 16-byte aligned, ZERO-FILLED ONCE after
+ *              allocation (the kernel leaves its counters at zero); one workspace per concurrently running stream
+ * Requirements: d % 64 == 0, h % 64 == 0, es % 4 == 0, E <= 512 and an expert size the tile shapes support;
+ * otherwise MOE_ERR_UNSUPPORTED_SHAPE is returned and the caller uses the three separate entry points.
+ * The kernel occupies every SM with one CTA and its CTAs wait on each other: it must not share the device with
+ * a kernel that never finishes (all CUDA kernels of this library do finish).
+ */
+MOE_API int moe_ffn_fused(const void* x, const void* w1p, const float* b1p, const void* w2p, const float* b2, void* H,
+                  float* scores, void* Y, const uint32_t* removed_bits, int k, uint32_t* active_bits, int16_t* idx,
+                  unsigned long long* hist, int count_begin, int count_end, int T, int d, int h, int E, int es, int act,
+                  int mask_h, void* workspace, size_t workspace_bytes, void* stream);
+MOE_API size_t moe_ffn_fused_workspace_bytes(int T, int d, int h);
+/* Profiling hook of the fused kernel (library built with -DMOE_TRACE=1 only): per-CTA %globaltimer stamps. */
+MOE_API int moe_debug_trace_fused(unsigned long long* host_out, int n);
+
 /* Profiling hook: with the environment variable MOE_DEBUG_MODE bit 16 set, the GEMM kernels record
  * per-CTA cycle counts of their producer / MMA-issue loops; this copies the first n counters
  * (8 per CTA: empty-wait, TMA-issue, iterations, acc-wait, full-wait, MMA-issue, commit, -) to a HOST
  * buffer.  Synchronises the device.  Not part of the hot path. */
 MOE_API int moe_debug_counters(unsigned long long* host_out, int n);
+/* Profiling hook: with MOE_DEBUG_MODE bit 32 set, each GEMM CTA stamps %globaltimer (ns) at fixed points
+ * (64 slots per CTA: entry, set-up done, first load, first MMA, per-tile commit / epilogue begin / end, exit);
+ * this copies the first n stamps to a HOST buffer.  Synchronises the device.  Not part of the hot path. */
+MOE_API int moe_debug_trace(unsigned long long* host_out, int n);
 
 #ifdef __cplusplus
 }

@@ -54,6 +54,28 @@ def cuda_layer(layer, ratio, act=O.ACT_GELU, removed=None, flags=None, want_gate
                 y=y.float().cpu().view(*lead, -1), k=k, E=E, es=es, sets=bits_to_sets(bits, E))
 
 
+def fused_layer(layer, ratio, act=O.ACT_GELU, removed=None, count_rows=None, repeats=1):
+    """The same layer through ONE moe_ffn_fused launch (K1 -> routing -> K3 in a persistent kernel)."""
+    lay = ExpertLayout.from_labels(layer["labels"])
+    E, es = lay.n_experts, lay.expert_size
+    k = O.topk_from_ratio(E, ratio)
+    p = pack_ffn(lay, layer["w1"], layer["b1"], layer["w2"], layer["b2"], device=DEV)
+    x = layer["x"]
+    lead = x.shape[:-1]
+    xt = x.reshape(-1, x.shape[-1]).to(DEV, torch.bfloat16).contiguous()
+    rb = None if not removed else M.bits_from_expert_list(removed, E).to(DEV)
+    rows = count_rows if count_rows is not None else (0, x.shape[-2])
+    for _ in range(repeats):
+        hist = torch.zeros(E, dtype=torch.int64, device=DEV)
+        y, H, scores, bits, idx = M.ffn_fused(xt, p.w1p, p.b1p, p.w2p, p.b2, E, es, k, act, removed_bits=rb,
+                                              want_bits=True, want_idx=True, hist=hist, count_rows=rows)
+    torch.cuda.synchronize()
+    inv = lay.inv_perm
+    return dict(H=H.float().cpu()[:, inv].view(*lead, -1), scores=scores.cpu(), idx=idx.cpu().long(), bits=bits.cpu(),
+                hist=hist.cpu(), y=y.float().cpu().view(*lead, -1), k=k, E=E, es=es, sets=bits_to_sets(bits, E),
+                colmax=scores.max(0)[0].cpu())
+
+
 def oracle_layer(layer, ratio, act=O.ACT_GELU, removed=None, timestep=0):
     """The oracle on the bf16-rounded weights / inputs (fp32 arithmetic)."""
     pat = O.patterns_from_labels(layer["labels"])

@@ -1,0 +1,111 @@
+"""GPU: the fused layer kernel (moe_ffn_fused: K1 -> in-kernel routing -> K3 in one persistent launch) against
+the oracle, against the three separate kernels, and for the cross-CTA hand-over protocol (repeat launches on the
+same workspace, ragged / tiny / odd row-block counts, split-K shapes)."""
+import numpy as np
+import pytest
+import torch
+
+import moe_b200 as M
+import moe_ffn_oracle as O
+from gpu_util import DEV, cuda_layer, fused_layer, oracle_layer, check_layer, rel_err, OUT_REL_TOL
+
+pytestmark = pytest.mark.gpu
+
+FUSED_CASES = [
+    # d, h, (B, S), es, ratio, act
+    (64, 256, (2, 48), 16, 0.3, O.ACT_GELU),        # one row block, one pair busy
+    (64, 256, (1, 1), 16, 0.5, O.ACT_RELU),         # single token
+    (64, 256, (3, 171), 16, 1.0, O.ACT_GELU),       # k == E (identity mask), ragged, odd number of row blocks
+    (128, 640, (1, 300), 20, 0.3, O.ACT_GELU),      # nv = 80 tiles, 3 row blocks
+    (320, 1280, (1, 1024), 20, 0.3, O.ACT_GELU),    # SD-1.5 down_blocks.0 geometry, reference experts
+    (320, 1280, (1, 1024), 64, 0.3, O.ACT_RELU),    # BASELINE-literal 20 experts of 64 (tpt = 2)
+    (640, 2560, (2, 256), 20, 0.3, O.ACT_GELU),     # split-K down-projection
+    (1280, 5120, (2, 64), 20, 0.3, O.ACT_GELU),     # mid-block geometry: E = 256 (tpt = 16), one row block
+    (1280, 5120, (2, 256), 20, 0.1, O.ACT_GELU),    # d = 1280 at 512 tokens: 4 chunks per block
+]
+
+
+@pytest.mark.parametrize("d,h,shape,es,ratio,act", FUSED_CASES)
+def test_fused_layer_matches_oracle(lib, d, h, shape, es, ratio, act):
+    layer = O.synthetic_layer(d, h, shape, es, seed=d + es)
+    cu = fused_layer(layer, ratio, act)
+    orc = oracle_layer(layer, ratio, act)
+    stats = check_layer(cu, orc, min_safe_fraction=0.85)
+    S = shape[1]
+    assert torch.equal(cu["hist"], torch.bincount(cu["idx"][:S].reshape(-1), minlength=cu["E"]))
+    assert int(cu["hist"].sum()) == S * cu["k"]
+    # labels ascending and consistent with the expert-set words
+    assert (cu["idx"][:, 1:] > cu["idx"][:, :-1]).all() or cu["k"] <= 1
+    assert [set(r.tolist()) for r in cu["idx"]] == cu["sets"]
+    print(stats)
+
+
+def test_fused_config1_full_size_matches_unfused_and_oracle(lib):
+    """BASELINE configs[0] at full size (d 320, 2 x 4096 tokens, 64 experts of 20, k = 19)."""
+    layer = O.synthetic_layer(320, 1280, (2, 4096), 20, seed=1)
+    fu = fused_layer(layer, 0.3)
+    un = cuda_layer(layer, 0.3)
+    orc = oracle_layer(layer, 0.3)
+    check_layer(fu, orc)
+    # fused vs separate kernels: same scores up to summation order, identical routing away from ties
+    assert torch.allclose(fu["scores"], un["scores"], atol=1e-4, rtol=1e-5)
+    margin = O.topk_margin(un["scores"], un["k"]).numpy()
+    agree = np.array([a == b for a, b in zip(fu["sets"], un["sets"])])
+    assert agree[margin > 1e-3].all()
+    assert rel_err(fu["y"].reshape(-1, 320)[agree], un["y"].reshape(-1, 320)[agree]) < 2e-3
+    assert int(fu["hist"].sum()) == 4096 * 19
+
+
+def test_fused_removed_experts_and_count_window(lib):
+    """RemoveExperts rule inside the fused kernel: removed experts score exactly 0, still compete, own no neurons
+    (remove_skilled_experts.py:29-49); the histogram counts the rows of the given window only."""
+    layer = O.synthetic_layer(320, 1280, (2, 512), 20, seed=5)
+    removed = [0, 7, 13, 31, 32, 63]
+    cu = fused_layer(layer, 0.3, removed=removed, count_rows=(100, 700))
+    un = cuda_layer(layer, 0.3, removed=removed, count_rows=(100, 700))
+    orc = oracle_layer(layer, 0.3, removed=removed, timestep=0)
+    want = [set(r.tolist()) for r in orc["labels"].reshape(-1, orc["labels"].shape[-1])]
+    safe = (orc["margin"] > 2e-3).numpy()
+    n = len(want)
+    got = [set(r.tolist()) for r in cu["idx"]]                    # labels include removed experts that took a slot
+    agree = np.array([got[i] == want[i] for i in range(n)])
+    assert safe.mean() > 0.85 and agree[safe].all()
+    for t in range(n):
+        assert cu["sets"][t] == got[t] - set(removed)             # active set = selected and not removed
+    Hc, Ho = cu["H"].reshape(n, -1), orc["H"].reshape(n, -1)
+    assert rel_err(Hc[agree], Ho[agree]) < OUT_REL_TOL
+    assert rel_err(cu["y"].reshape(n, -1)[agree], orc["y"].reshape(n, -1)[agree]) < OUT_REL_TOL
+    dead = orc["pat"][removed].sum(0) > 0
+    assert torch.all(Hc[:, dead] == 0)                            # removed experts' neurons are always masked
+    assert torch.equal(cu["hist"], torch.bincount(cu["idx"][100:700].reshape(-1), minlength=64))
+    # same routing as the separate router kernel on (nearly) the same scores
+    same = np.array([a == b for a, b in zip(cu["sets"], un["sets"])])
+    assert same[O.topk_margin(un["scores"], un["k"]).numpy() > 1e-3].all()
+
+
+def test_fused_repeat_launches_share_workspace(lib):
+    """The sync counters are left at zero by every launch: back-to-back launches on one workspace, of different
+    geometries, give the same results as fresh ones."""
+    a = O.synthetic_layer(320, 1280, (2, 700), 20, seed=3)
+    b = O.synthetic_layer(640, 2560, (1, 130), 20, seed=4)
+    first_a = fused_layer(a, 0.3)
+    first_b = fused_layer(b, 0.3)
+    again_a = fused_layer(a, 0.3, repeats=5)
+    again_b = fused_layer(b, 0.3, repeats=3)
+    for x, y in ((first_a, again_a), (first_b, again_b)):
+        assert torch.equal(x["scores"], y["scores"])
+        assert torch.equal(x["idx"], y["idx"])
+        assert torch.equal(x["H"], y["H"])
+        assert torch.equal(x["y"], y["y"])            # deterministic, including the split-K reduction order
+        assert torch.equal(x["hist"], y["hist"])
+    ws = M.fused_workspace(DEV, 1)
+    torch.cuda.synchronize()
+    assert int(ws[: 4 * (16 + 3 * 16384)].view(torch.int32).abs().sum()) == 0
+
+
+def test_fused_unsupported_geometry_raises(lib):
+    x = torch.zeros(8, 40, dtype=torch.bfloat16, device=DEV)
+    w1 = torch.zeros(320, 40, dtype=torch.bfloat16, device=DEV)
+    w2 = torch.zeros(40, 160, dtype=torch.bfloat16, device=DEV)
+    with pytest.raises(M._lib.MoeLibraryError, match="multiples of 64"):
+        M.ffn_fused(x, w1, None, w2, None, 20, 8, 5)
