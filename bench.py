@@ -61,6 +61,8 @@ def parse():
     ap.add_argument("--batch", type=int, default=2, help="UNet batch (2 = one prompt with CFG)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--path", default="fused", choices=["fused", "split"],
+                    help="fused: one moe_ffn_fused launch per layer; split: K1 -> K2 -> K3 launches")
     return ap.parse_args()
 
 
@@ -189,7 +191,16 @@ def gpu_arm(args):
     hist_host = torch.zeros(len(layers), e_max, dtype=torch.int64).pin_memory()
     tokens_per_step = sum(L["T"] for L in layers)
 
+    fused = args.path == "fused"
+
     def ffn_step(record=None):
+        if fused:
+            for li, L in enumerate(layers):
+                p = L["p"]
+                M.ffn_fused(L["x"], p.w1p, p.b1p, p.w2p, p.b2, L["E"], L["es"], L["k"], M.ACT_GELU,
+                            hist=hist[li, :L["E"]], count_rows=(0, L["s"]), H_out=L["H"], scores_out=L["scores"],
+                            out=L["y"])
+            return
         for li, L in enumerate(layers):
             p = L["p"]
             if record is not None:
@@ -214,7 +225,7 @@ def gpu_arm(args):
     for _ in range(max(3, args.warmup)):
         ffn_step()
     torch.cuda.synchronize()
-    launches_per_step = 3 * len(layers)
+    launches_per_step = (1 if fused else 3) * len(layers)
 
     graph = None
     if not args.no_graph:
@@ -276,7 +287,7 @@ def gpu_arm(args):
 
     per_kernel = []
     n_inst = max(5, min(args.steps, 20))
-    for kind in range(3):
+    for kind in range(0 if fused else 3):
         gk = torch.cuda.CUDAGraph()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -341,9 +352,18 @@ def gpu_arm(args):
     except (OSError, ValueError):
         peaks = {"bf16_tflops_sustained": 1400.0, "bf16_tflops": 1590.0, "hbm_gbs": 6650.0}
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))   # kernel timed inside a long step
-    k1_tf = k1_flops / (per_kernel[0] * 1e-3) / 1e12
-    k3_tf = k3_flops / (per_kernel[2] * 1e-3) / 1e12
-    roofline = dict(bound="tensor", kernel="geglu_up_kernel (K1)", achieved=round(k1_tf, 2), peak=peak_tf,
+    if fused:
+        # the step IS the dominant kernel: 16 launches of ffn_fused_kernel, nothing else in the timed region
+        tf = (k1_flops + k3_flops) / (ms_step * 1e-3) / 1e12
+        roofline = dict(bound="tensor", kernel="ffn_fused_kernel (K1 + routing + K3 per layer)", achieved=round(tf, 2),
+                        peak=peak_tf, unit="TFLOP/s", frac=round(tf / peak_tf, 4), traffic=None, peak_source=peak_src,
+                        algorithmic="6*d*h FLOP per token (4dh up-projection + 2dh dense-equivalent down-projection), "
+                                    "summed over the step's 16 launches / the step time (CUDA events; the timed region "
+                                    "holds nothing but these launches)")
+    else:
+      k1_tf = k1_flops / (per_kernel[0] * 1e-3) / 1e12
+      k3_tf = k3_flops / (per_kernel[2] * 1e-3) / 1e12
+      roofline = dict(bound="tensor", kernel="geglu_up_kernel (K1)", achieved=round(k1_tf, 2), peak=peak_tf,
                     unit="TFLOP/s", frac=round(k1_tf / peak_tf, 4),
                     # ncu --set full, dram__bytes_read + write of the config-1 K1 launch (d=320, 8192 tokens; its
                     # algorithmic bytes are 30 MB, of which the 21 MB H tile stays in L2): profiles/r01_ncu_full_v6_*
@@ -363,7 +383,8 @@ def gpu_arm(args):
                                     f"top-k ratio {RATIO}",
                             tokens_per_step_per_gpu=tokens_per_step, parallelism=f"prompt-sharded x{world}",
                             l2="working set ~0.5 GB per step > 126 MB L2; no explicit flush",
-                            cuda_graph=graph is not None, counters="row-0 expert histogram fused in K2"),
+                            cuda_graph=graph is not None, path=args.path,
+                            counters="row-0 expert histogram fused in the routing stage"),
                 unet_steps_per_s=world * 1e3 / ms_step,
                 e2e=dict(value=world * tokens_per_step / (ms_e2e * 1e-3), unit="tokens/s", h2d_bytes_per_step=h2d,
                          d2h_bytes_per_step=d2h, ms_per_step=ms_e2e),

@@ -8,7 +8,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libmoe_b200.so")
+_VARIANT = os.environ.get("MOE_LIB_VARIANT", "")     # "trace": profiling build (tools/ only), see build.py
+LIB_PATH = os.path.join(_HERE, "lib", "libmoe_b200" + (("_" + _VARIANT) if _VARIANT else "") + ".so")
 
 c_void_p, c_int, c_float, c_ll = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_longlong
 

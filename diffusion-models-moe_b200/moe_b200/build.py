@@ -12,8 +12,11 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
-LIB_PATH = os.path.join(LIB_DIR, "libmoe_b200.so")
-STAMP = os.path.join(LIB_DIR, "libmoe_b200.stamp")
+# MOE_LIB_VARIANT=trace builds / loads a second library with the in-kernel timeline stamps compiled in (tools/ only)
+VARIANT = os.environ.get("MOE_LIB_VARIANT", "")
+_SUFFIX = ("_" + VARIANT) if VARIANT else ""
+LIB_PATH = os.path.join(LIB_DIR, f"libmoe_b200{_SUFFIX}.so")
+STAMP = os.path.join(LIB_DIR, f"libmoe_b200{_SUFFIX}.stamp")
 INCLUDE = os.path.normpath(os.path.join(HERE, "..", "..", "include"))
 
 NVCC_FLAGS = [
@@ -21,7 +24,7 @@ NVCC_FLAGS = [
     "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
     "--shared", "-cudart", "static",
-]
+] + (["-DMOE_TRACE=1"] if VARIANT == "trace" else [])
 
 
 def sources():

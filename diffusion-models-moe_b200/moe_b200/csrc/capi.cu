@@ -40,6 +40,11 @@ static EncodeTiledFn encode_fn() {
 
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
                       uint32_t box_cols, bool swizzle128) {
+  return make_tmap_bf16_2d_sw(out, base, rows, cols, box_rows, box_cols, swizzle128 ? 128 : 0);
+}
+
+int make_tmap_bf16_2d_sw(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                         uint32_t box_cols, int swizzle_bytes) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail(MOE_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (cols * 2) % 16 != 0)
@@ -50,7 +55,11 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle_bytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
+                  : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                  : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                        : CU_TENSOR_MAP_SWIZZLE_NONE,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(MOE_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);

@@ -10,15 +10,20 @@
 //
 // CTA pairs (clusters of 2, one CTA per SM, grid = all SMs) walk a static work list: first their phase-1
 // tiles (256 token rows x nv neuron pairs), then their phase-3 items (256 rows x bn outputs x one K slice).
-// Cross-CTA dependencies go through three int arrays in a small global workspace, per 128-row block m:
-//     done[m]    += 1 for every phase-1 tile of the block whose H tile (TMA store) and scores are written
-//     ticket[m]  hands out the block's routing chunks (one chunk = 512 / tpt tokens = one pass of the 16
-//                epilogue warps) to whichever CTA asks first: the CTA that completed the block, or a CTA
-//                that is about to need the block in phase 3
+// Cross-CTA dependencies go through a small global sync area, per 128-row block m:
+//     done[m]    += 1 for every phase-1 tile of the block whose H tile (TMA store) and scores are written; 
+//     routing    the block's phase-3 items ("consumers") split its routing chunks among themselves statically
+//                (consumer r takes chunks r, r + consumers, ...) and route them with their 16 epilogue warps before
+//                their own main loop; nothing is routed while phase 1 runs.  (A global work queue with
+//                compare-and-swap tickets was tried: 148 CTAs hammering one L2 line serialised it completely.)
 //     ready[m]   += 1 per routed chunk; a phase-3 A-tile producer waits for ready[m] == chunks per block
+// Masking (the reference's gate[mask == 0] = 0) is write-only: the routing stage zeroes the neurons of inactive
+// experts in H with 16-byte stores, a whole warp per token row, spread over the block's consumer CTAs.  (Masking
+// the landed H tiles in shared memory inside the phase-3 pipeline was tried and measured: the extra
+// wait / fence / cluster-arrive per stage cost ~1 us per stage, three times the main loop itself.)
 // All CTAs are co-resident (grid <= SM count, 1 CTA / SM) and every CTA finishes its phase-1 tiles, which
 // never wait on another CTA, before it waits for anything, so the waits cannot deadlock.  The last CTA to
-// exit zeroes the arrays again (the workspace must be zero before the first launch).
+// exit zeroes the sync area again (the workspace must be zero before the first launch).
 //
 // Warp roles (640 threads):
 //   warp 0      A-tile TMA producer (x in phase 1, H in phase 3 -- waits for ready[m])
@@ -27,7 +32,7 @@
 //               staging buffers, publishes done[m], claims routing chunks and posts them to the epilogue warps
 //   warp 3      B-tile TMA producer (W1 / W2 slices; weights have no dependencies, so it runs ahead)
 //   warps 4-19  epilogue: TMEM -> registers -> bias / exact GELU / product (packed f32x2 math) -> bf16 ->
-//               smem staging; expert scores; routing chunks on request; split-K partials and reduction
+//               smem staging; expert scores; routing chunks on request; phase-3 maskers; split-K reduction
 #include "common.cuh"
 #include "tcgen05.cuh"
 
@@ -52,12 +57,14 @@ constexpr int kMaxStages = 8;
 constexpr int kSmemLimit = 232448;
 constexpr int kBiasBytesPerWarp = 128 * 4;          // 2 x 64 floats
 constexpr int kSpartPerRow = 8;                      // partial / per-expert score slots per token row and tile
-constexpr int kKeys = 16;                            // experts per routing thread
-constexpr int kRouteWordsPerWarp = 32;
-constexpr int kMaxExperts = 512;
-constexpr int kSyncHeaderInts = 16;                  // [0] exit counter
-constexpr int kMaxBlocks = 16384;                    // 128-row blocks the sync arrays can hold
-constexpr size_t kSyncBytes = (kSyncHeaderInts + 3 * static_cast<size_t>(kMaxBlocks)) * 4;
+constexpr int kMaxWords = 8;                         // expert-set words per token (E <= 256)
+constexpr int kMaxExperts = 32 * kMaxWords;
+// sync area (ints): header {exit counter}, then one 128-byte record per 128-row block {done, ready} (separate
+// cache lines: pollers of different blocks do not serialise on one L2 line)
+constexpr int kSyncHeaderInts = 32;
+constexpr int kBlockRecInts = 32;
+constexpr int kMaxBlocks = 2048;                     // 128-row blocks (T <= 262144 tokens)
+constexpr size_t kSyncBytes = (kSyncHeaderInts + static_cast<size_t>(kMaxBlocks) * kBlockRecInts) * 4;
 constexpr size_t kSplitCounterBytes = 64 * 1024;
 
 #if MOE_TRACE
@@ -81,7 +88,6 @@ struct Barriers {
   uint64_t hs_empty[2];    // staging buffer stored by the sync warp
   uint64_t route_req;      // sync warp -> epilogue warps: a routing chunk is posted
   uint64_t route_done;     // 16 epilogue warps -> sync warp
-  uint64_t fin;            // sync warp has nothing more to post
   uint32_t tmem_base;
   int req_block, req_chunk;
   int last_cta;
@@ -98,7 +104,10 @@ struct Shape {
   // pipeline
   int stages, slot_bytes, hs_bytes;             // hs_bytes: one phase-1 staging buffer (two of them; phase 3 uses both)
   // routing
-  int tpt, tpt_log2, chunks_per_block;          // threads per token; chunk = 512 / tpt tokens
+  int lanes, lanes_log2;                        // lanes per token in the routing stage (4, 8 or 16)
+  int kpt;                                      // experts per routing lane: ceil(E / lanes) rounded up to a power of two
+  int chunk_tokens, chunks_per_block;           // chunk = 512 / lanes tokens = one pass of the 16 epilogue warps
+  int words;                                    // expert-set words per token
   int act, mask_h, count_begin, count_end;
   uint32_t es_magic;
 };
@@ -113,7 +122,7 @@ struct Ptrs {
   uint32_t* active_bits;
   int16_t* idx;
   unsigned long long* hist;
-  int* sync;                // [kSyncHeaderInts] header | done[] | ticket[] | ready[]
+  int* sync;                // header | per-block records | routing queue
   int* split_counters;
   float* split_partial;
 };
@@ -180,8 +189,10 @@ template <int ACT>
 __device__ __forceinline__ uint64_t activate2(float x0, float x1) {
   if constexpr (ACT == MOE_ACT_GELU)
     return gelu2(x0, x1);
-  else
+  else if constexpr (ACT == MOE_ACT_RELU)
     return pk2(fmaxf(x0, 0.f), fmaxf(x1, 0.f));
+  else
+    return pk2(x0, x1);   // profiling only (trace build): no activation math
 }
 
 // order-preserving float -> uint32 key (ascending)
@@ -226,49 +237,79 @@ __device__ __forceinline__ bool item3(const Shape& g, int it, int p, int P, int 
 }
 
 // ------------------------------------------------------------------------------------------ routing
-// One chunk = 512 / tpt consecutive tokens; `tpt` consecutive lanes own one token, each lane 16 experts.
-// Exact k-th largest score by bisection on the order-preserving integer keys (MSB first, starting below the
-// key prefix the whole warp shares, stopping when every token of the warp has separated exactly k keys);
-// ties on the k-th key go to the lowest expert ids.  Outputs: expert-set words, ascending labels, histogram
-// (shared-memory bins), and write-only masking of H (16-byte zero stores, a whole warp per token row).
+// One chunk = 32 consecutive tokens of one 128-row block; 16 lanes own one token (2 tokens per warp), each lane
+// KPT consecutive experts.  Exact k-th largest score by bisection on the order-preserving integer keys (MSB first,
+// starting below the key prefix the whole warp shares, stopping as soon as both tokens of the warp have separated
+// exactly k keys); ties on the k-th key go to the lowest expert ids.  Outputs: expert-set words (what the
+// down-projection masks with), ascending labels, histogram (shared-memory bins) and, only when the caller wants
+// the masked hidden state materialised, write-only zeroing of H (16-byte stores, a whole warp per token row).
+template <int KPT>
 __device__ __forceinline__ void route_chunk(const Shape& g, const Ptrs& a, int tok0, int tok_end, int ew, int lane,
                                             uint32_t* s_words, unsigned int* s_hist) {
   const unsigned full = 0xffffffffu;
-  const int tpt = g.tpt;
-  const int tpw = 32 >> g.tpt_log2;            // tokens per warp
-  const int part = lane & (tpt - 1);
-  const int tl = lane >> g.tpt_log2;
-  const int t = tok0 + ew * tpw + tl;
+  const int L = g.lanes;
+  const int tpw = 32 >> g.lanes_log2;           // tokens per warp
+  const int part = lane & (L - 1);
+  const int tl = lane >> g.lanes_log2;
+  // per-token sums over the token's L lanes with full-warp REDUX instructions: every token of the warp owns a
+  // bit field of the reduced word (16 bits for 2 tokens per warp, 8 bits for 4 or 8 tokens -- 8 tokens take two
+  // reductions); a field never overflows because a token has at most E <= 16 L experts.  (A reduction over a
+  // per-token member mask compiles to a divergent slow path: ~550 cycles per bisection round.)
+  const int fshift = (tpw <= 2) ? 16 * tl : 8 * (tl & 3);
+  const uint32_t fmask = (tpw == 1) ? 0xffffffffu : (tpw == 2) ? 0xffffu : 0xffu;
+  auto token_sum = [&](int c) -> int {
+    const uint32_t v = static_cast<uint32_t>(c) << fshift;
+    uint32_t r;
+    if (tpw == 8) {
+      const uint32_t r0 = __reduce_add_sync(full, tl < 4 ? v : 0u);
+      const uint32_t r1 = __reduce_add_sync(full, tl < 4 ? 0u : v);
+      r = tl < 4 ? r0 : r1;
+    } else {
+      r = __reduce_add_sync(full, v);
+    }
+    return static_cast<int>((r >> fshift) & fmask);
+  };
+  const int t = tok0 + tpw * ew + tl;
   const bool t_ok = t < tok_end;   // tok_end <= T: end of the 128-row block (a chunk never leaves its block)
-  const int e0 = part * kKeys;
+  const int e0 = part * KPT;
   const int E = g.E;
 
-  uint32_t key[kKeys];
-  uint32_t valid = 0u;
+  uint32_t key[KPT];
+  uint32_t valid = 0u, removed = 0u;
+  if (a.removed_bits != nullptr && e0 < E) removed = (__ldg(a.removed_bits + (e0 >> 5)) >> (e0 & 31)) & ((KPT == 32) ? ~0u : ((1u << KPT) - 1u));
   {
-    uint32_t removed = 0u;
-    if (a.removed_bits != nullptr && e0 < E) removed = (__ldg(a.removed_bits + (e0 >> 5)) >> (e0 & 31)) & 0xffffu;
     const float* row = a.scores + static_cast<size_t>(t_ok ? t : 0) * E + e0;
-    if ((E & 3) == 0) {
+    if constexpr (KPT % 4 == 0) {
+      if ((E & 3) == 0) {
 #pragma unroll
-      for (int i4 = 0; i4 < kKeys / 4; ++i4) {
-        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-        const bool in = t_ok && (e0 + 4 * i4) < E;
-        if (in) {
-          s = __ldcg(reinterpret_cast<const float4*>(row + 4 * i4));
-          valid |= 0xfu << (4 * i4);
+        for (int i4 = 0; i4 < KPT / 4; ++i4) {
+          float4 sc = make_float4(0.f, 0.f, 0.f, 0.f);
+          const bool in = t_ok && (e0 + 4 * i4) < E;
+          if (in) {
+            sc = __ldcg(reinterpret_cast<const float4*>(row + 4 * i4));
+            valid |= 0xfu << (4 * i4);
+          }
+          const float sv[4] = {sc.x, sc.y, sc.z, sc.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int i = 4 * i4 + j;
+            const float v = ((removed >> i) & 1u) ? 0.f : sv[j];   // zeroed pattern row => score exactly 0
+            key[i] = in ? float_key(v) : 0u;
+          }
         }
-        const float sv[4] = {s.x, s.y, s.z, s.w};
+      } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int i = 4 * i4 + j;
-          const float v = ((removed >> i) & 1u) ? 0.f : sv[j];   // zeroed pattern row => score exactly 0
+        for (int i = 0; i < KPT; ++i) {
+          const bool in = t_ok && (e0 + i) < E;
+          float v = in ? __ldcg(row + i) : 0.f;
+          if ((removed >> i) & 1u) v = 0.f;
           key[i] = in ? float_key(v) : 0u;
+          if (in) valid |= 1u << i;
         }
       }
     } else {
 #pragma unroll
-      for (int i = 0; i < kKeys; ++i) {
+      for (int i = 0; i < KPT; ++i) {
         const bool in = t_ok && (e0 + i) < E;
         float v = in ? __ldcg(row + i) : 0.f;
         if ((removed >> i) & 1u) v = 0.f;
@@ -277,54 +318,81 @@ __device__ __forceinline__ void route_chunk(const Shape& g, const Ptrs& a, int t
       }
     }
   }
+#if MOE_TRACE
+  if (ew == 0 && lane == 0) TRACE(56);
+#endif
 
-  uint32_t sel = 0u;   // 16-bit mask over this lane's experts
+  uint32_t sel = 0u;   // KPT-bit mask over this lane's experts
   if (g.k >= E) {
     sel = valid;
   } else if (g.k > 0) {
-    // common key prefix of the warp's valid keys
-    uint32_t k_or = 0u, k_and = full;
+    // k-th largest key of the token: bitonic sort of its N = KPT * L keys (element i = part * KPT + r; invalid
+    // slots hold key 0 and sink to the bottom), compare-exchanges inside a lane for distances < KPT and through
+    // shuffles beyond.  ~250 instructions and ~700 cycles per pass regardless of the data; the MSB-first bisection
+    // this replaces needed ~20 dependent REDUX + VOTE rounds (3-6 us per pass).
+    uint32_t srt[KPT];
 #pragma unroll
-    for (int i = 0; i < kKeys; ++i)
-      if ((valid >> i) & 1u) {
-        k_or |= key[i];
-        k_and &= key[i];
-      }
-    k_or = __reduce_or_sync(full, k_or);
-    k_and = __reduce_and_sync(full, k_and);
-    const uint32_t diff = k_or ^ k_and;
-    uint32_t prefix = 0u;
-    bool exact = !t_ok;   // idle token slots never hold the warp back
-    if (diff != 0u) {
-      const int top = 31 - __clz(diff);
-      prefix = (top == 31) ? 0u : (k_and & ~((2u << top) - 1u));
-      for (int bit = top; bit >= 0; --bit) {
-        const uint32_t thr = prefix | (1u << bit);
-        int c = 0;
+    for (int r = 0; r < KPT; ++r) srt[r] = key[r];
+    // sizes up to KPT: entirely inside the lane, directions known at compile time except for size == KPT ... N
 #pragma unroll
-        for (int i = 0; i < kKeys; ++i) c += (key[i] >= thr) ? 1 : 0;
-        for (int o = 1; o < tpt; o <<= 1) c += __shfl_xor_sync(full, c, o);
-        if (c >= g.k) prefix = thr;
-        exact = exact || (c == g.k);
-        if (__all_sync(full, exact)) break;
+    for (int size = 2; size <= KPT; size <<= 1) {
+      const bool lane_up = ((part * KPT) & size) == 0;   // only matters for size == KPT's parent bit: (i & size)
+#pragma unroll
+      for (int stride = size >> 1; stride >= 1; stride >>= 1) {
+#pragma unroll
+        for (int r = 0; r < KPT; ++r) {
+          if ((r & stride) == 0) {
+            const bool up = (size < KPT) ? ((r & size) == 0) : lane_up;
+            const uint32_t lo = min(srt[r], srt[r | stride]), hi = max(srt[r], srt[r | stride]);
+            srt[r] = up ? lo : hi;
+            srt[r | stride] = up ? hi : lo;
+          }
+        }
       }
-    } else {
-      prefix = k_and;   // every valid key of the warp is identical
     }
+    // sizes beyond one lane: lane distances L' = size / KPT / 2 ... 1 through shuffles, then the in-lane strides
+    for (int lsize = 2; lsize <= L; lsize <<= 1) {        // size = lsize * KPT
+      const bool up = (part & lsize) == 0 || lsize == L;   // the last merge sorts everything ascending
+      for (int ls = lsize >> 1; ls >= 1; ls >>= 1) {
+        const bool lower = (part & ls) == 0;
+        const bool keep_min = lower == up;
+#pragma unroll
+        for (int r = 0; r < KPT; ++r) {
+          const uint32_t other = __shfl_xor_sync(full, srt[r], ls);
+          srt[r] = keep_min ? min(srt[r], other) : max(srt[r], other);
+        }
+      }
+#pragma unroll
+      for (int stride = KPT >> 1; stride >= 1; stride >>= 1) {
+#pragma unroll
+        for (int r = 0; r < KPT; ++r) {
+          if ((r & stride) == 0) {
+            const uint32_t lo = min(srt[r], srt[r | stride]), hi = max(srt[r], srt[r | stride]);
+            srt[r] = up ? lo : hi;
+            srt[r | stride] = up ? hi : lo;
+          }
+        }
+      }
+    }
+    // ascending over the token's lanes: the k-th largest sits at element N - k
+    const int pos = KPT * L - g.k;
+    uint32_t mine = 0u;
+#pragma unroll
+    for (int r = 0; r < KPT; ++r) mine = (r == (pos & (KPT - 1))) ? srt[r] : mine;
+    const uint32_t prefix = __shfl_sync(full, mine, (lane & ~(L - 1)) + pos / KPT);
     // keys above the k-th value, then ties on it from the lowest expert id
     uint32_t gt = 0u, eq = 0u;
 #pragma unroll
-    for (int i = 0; i < kKeys; ++i) {
+    for (int i = 0; i < KPT; ++i) {
       const bool v = (valid >> i) & 1u;
       gt |= (v && key[i] > prefix) ? (1u << i) : 0u;
       eq |= (v && key[i] == prefix) ? (1u << i) : 0u;
     }
-    int n_gt = __popc(gt);
-    for (int o = 1; o < tpt; o <<= 1) n_gt += __shfl_xor_sync(full, n_gt, o);
+    const int n_gt = token_sum(__popc(gt));
     const int n_eq = __popc(eq);
     int incl = n_eq;
-    for (int o = 1; o < tpt; o <<= 1) {
-      const int v = __shfl_up_sync(full, incl, o, tpt);
+    for (int o = 1; o < L; o <<= 1) {
+      const int v = __shfl_up_sync(full, incl, o, L);
       if (part >= o) incl += v;
     }
     int take = g.k - n_gt - (incl - n_eq);
@@ -337,25 +405,26 @@ __device__ __forceinline__ void route_chunk(const Shape& g, const Ptrs& a, int t
     }
     sel = gt | ties;
   }
+#if MOE_TRACE
+  if (ew == 0 && lane == 0) TRACE(57);
+#endif
 
-  uint32_t removed16 = 0u;
-  if (a.removed_bits != nullptr && e0 < E) removed16 = (__ldg(a.removed_bits + (e0 >> 5)) >> (e0 & 31)) & 0xffffu;
-  const uint32_t active = sel & ~removed16;
-
-  // expert-set words: lanes with an even part own a 32-bit word
-  const uint32_t hi = __shfl_down_sync(full, active, 1);
-  const uint32_t word = (tpt > 1) ? (active | (hi << 16)) : active;
-  const int words_per_token = (E + 31) >> 5;
-  if ((part & 1) == 0 && (part >> 1) < words_per_token) {
-    s_words[tl * words_per_token + (part >> 1)] = word;
-    if (a.active_bits != nullptr && t_ok) a.active_bits[static_cast<size_t>(t) * words_per_token + (part >> 1)] = word;
+  // expert-set words: OR the lanes' masks of each 32-expert word together (butterfly inside the word's lanes)
+  const uint32_t active = sel & ~removed;
+  const int lanes_per_word = (32 / KPT) < L ? (32 / KPT) : L;
+  uint32_t word = active << ((part * KPT) & 31);
+  for (int o = 1; o < lanes_per_word; o <<= 1) word |= __shfl_xor_sync(full, word, o);
+  const int widx = (part * KPT) >> 5;
+  if ((part & (lanes_per_word - 1)) == 0 && widx < g.words) {
+    s_words[tl * g.words + widx] = word;
+    if (t_ok && a.active_bits != nullptr) a.active_bits[static_cast<size_t>(t) * g.words + widx] = word;
   }
 
   if (a.idx != nullptr) {
     const int n_sel = __popc(sel);
     int incl = n_sel;
-    for (int o = 1; o < tpt; o <<= 1) {
-      const int v = __shfl_up_sync(full, incl, o, tpt);
+    for (int o = 1; o < L; o <<= 1) {
+      const int v = __shfl_up_sync(full, incl, o, L);
       if (part >= o) incl += v;
     }
     if (t_ok) {
@@ -378,15 +447,18 @@ __device__ __forceinline__ void route_chunk(const Shape& g, const Ptrs& a, int t
     }
   }
   __syncwarp();
+#if MOE_TRACE
+  if (ew == 0 && lane == 0) TRACE(58);
+#endif
 
   if (g.mask_h && g.k < E) {
-    // write-only masking: zero the neurons of every expert outside the token's active set (H is never read);
-    // 16-byte units, one token row per warp trip, 4-neuron groups never straddle an expert (es % 4 == 0)
+    // materialise the masked hidden state: zero the neurons of every expert outside the token's active set
+    // (write-only; 16-byte units, 4-neuron groups never straddle an expert because es % 4 == 0)
     const int units = g.h >> 3;
     for (int tt = 0; tt < tpw; ++tt) {
-      const int tok = tok0 + ew * tpw + tt;
+      const int tok = tok0 + tpw * ew + tt;
       if (tok >= tok_end) break;
-      const uint32_t* wtok = s_words + tt * words_per_token;
+      const uint32_t* wtok = s_words + tt * g.words;
       uint4* hrow = reinterpret_cast<uint4*>(a.H + static_cast<size_t>(tok) * g.h);
       for (int u = lane; u < units; u += 32) {
         const uint32_t ea = __umulhi(static_cast<uint32_t>(u) << 3, g.es_magic);
@@ -403,6 +475,21 @@ __device__ __forceinline__ void route_chunk(const Shape& g, const Ptrs& a, int t
     }
   }
   __syncwarp();
+#if MOE_TRACE
+  if (ew == 0 && lane == 0) TRACE(59);
+#endif
+}
+
+__device__ __forceinline__ void route_dispatch(const Shape& g, const Ptrs& a, int tok0, int tok_end, int ew, int lane,
+                                               uint32_t* s_words, unsigned int* s_hist) {
+  switch (g.kpt) {
+    case 16: route_chunk<16>(g, a, tok0, tok_end, ew, lane, s_words, s_hist); break;
+    case 8: route_chunk<8>(g, a, tok0, tok_end, ew, lane, s_words, s_hist); break;
+    case 4: route_chunk<4>(g, a, tok0, tok_end, ew, lane, s_words, s_hist); break;
+    case 2: route_chunk<2>(g, a, tok0, tok_end, ew, lane, s_words, s_hist); break;
+    case 1: route_chunk<1>(g, a, tok0, tok_end, ew, lane, s_words, s_hist); break;
+    default: break;
+  }
 }
 
 // ------------------------------------------------------------------------------------------ the kernel
@@ -428,9 +515,51 @@ __device__ __forceinline__ void store_words(void* dst, const uint32_t* w) {
   }
 }
 
+// Output staging tiles (H in phase 1, Y in phase 3) are kept in the layout the TMA store expects with swizzling:
+// 64-column panels ([128 rows][128 bytes], 128-byte swizzle) followed by one remainder panel of W % 64 columns
+// (64- / 32-byte swizzle when it is 32 / 16 columns wide).  A thread owns one row, so a warp's store hits 32
+// consecutive rows at the same column: in a dense [128][W] tile that is an 8- or 16-way bank conflict on every
+// store, swizzled it is conflict-free.
+struct StageLayout {
+  int n_full;          // 64-column panels
+  int rem_cols;        // columns of the remainder panel (0 if none)
+  uint32_t rem_smask;  // swizzle mask of the remainder panel: ((byte >> 7) & rem_smask) << 4 is XORed in
+};
+__device__ __forceinline__ StageLayout stage_layout(int width) {
+  StageLayout l;
+  l.n_full = width >> 6;
+  l.rem_cols = width & 63;
+  l.rem_smask = l.rem_cols == 32 ? 3u : (l.rem_cols == 16 ? 1u : 0u);
+  return l;
+}
+// shared-memory address of columns [x, x + 4) (x a multiple of 4, warp-uniform) of row r
+__device__ __forceinline__ uint32_t stage_addr(uint32_t base, const StageLayout& l, int r, int x) {
+  if (x < 64 * l.n_full)
+    return base + (x >> 6) * (kBlockM * 128) + r * 128 + ((((x & 63) * 2)) ^ ((r & 7) << 4));
+  const int pitch = l.rem_cols * 2;
+  const uint32_t lin = static_cast<uint32_t>(r * pitch);
+  return base + l.n_full * (kBlockM * 128) + lin + ((static_cast<uint32_t>(x - 64 * l.n_full) * 2u) ^ (((lin >> 7) & l.rem_smask) << 4));
+}
+// store kWords 32-bit words (2 columns each) starting at column x0: 16-byte stores on 8-column boundaries
+template <int kWords>
+__device__ __forceinline__ void stage_store(uint32_t base, const StageLayout& l, int r, int x0, const uint32_t* w) {
+  static_assert(kWords % 2 == 0, "whole 4-column pieces");
+  if ((x0 & 7) == 0) {
+#pragma unroll
+    for (int i = 0; i + 4 <= kWords; i += 4) tc::sts_b32x4(stage_addr(base, l, r, x0 + 2 * i), w[i], w[i + 1], w[i + 2], w[i + 3]);
+    if constexpr (kWords % 4 != 0) tc::sts_b32x2(stage_addr(base, l, r, x0 + 2 * (kWords - 2)), w[kWords - 2], w[kWords - 1]);
+  } else {
+    tc::sts_b32x2(stage_addr(base, l, r, x0), w[0], w[1]);
+#pragma unroll
+    for (int i = 2; i + 4 <= kWords; i += 4) tc::sts_b32x4(stage_addr(base, l, r, x0 + 2 * i), w[i], w[i + 1], w[i + 2], w[i + 3]);
+    if constexpr (kWords % 4 == 0) tc::sts_b32x2(stage_addr(base, l, r, x0 + 2 * (kWords - 2)), w[kWords - 2], w[kWords - 1]);
+  }
+}
+
 template <int CH, int ACT>
-__device__ __forceinline__ void geglu_group(const Shape& g, uint32_t taddr, const float* sbias, __nv_bfloat16* hrow,
-                                            float* spart_row, int col0, int cpg, int cg) {
+__device__ __forceinline__ void geglu_group(const Shape& g, uint32_t taddr, const float* sbias, uint32_t hbase,
+                                            const StageLayout& hl, int q_row, float* spart_row, int col0, int cpg,
+                                            int cg) {
   uint64_t score2 = pk2(0.f, 0.f);
   int chunk_in_expert = 0, e_slot = (g.chunks_per_expert > 0) ? cg * (cpg / g.es) : cg;
   for (int c = 0; c < cpg; c += CH) {
@@ -457,7 +586,7 @@ __device__ __forceinline__ void geglu_group(const Shape& g, uint32_t taddr, cons
       hw[i / 2] = pack_bf16x2(h0, h1);
       hw[i / 2 + 1] = pack_bf16x2(h2, h3);
     }
-    store_words<CH / 2>(hrow + col0 + c, hw);
+    stage_store<CH / 2>(hbase, hl, q_row, col0 + c, hw);
     if (g.chunks_per_expert > 0 && ++chunk_in_expert == g.chunks_per_expert) {
       float s0, s1;
       unpk2(score2, s0, s1);
@@ -477,8 +606,9 @@ template <int CH>
 __global__ void __launch_bounds__(kNumThreads, 1)
 ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w1,
                  const __grid_constant__ CUtensorMap tmap_hs, const __grid_constant__ CUtensorMap tmap_hl,
-                 const __grid_constant__ CUtensorMap tmap_w2, const __grid_constant__ CUtensorMap tmap_y, const Shape g,
-                 const Ptrs a) {
+                 const __grid_constant__ CUtensorMap tmap_w2, const __grid_constant__ CUtensorMap tmap_y,
+                 const __grid_constant__ CUtensorMap tmap_hs_rem, const __grid_constant__ CUtensorMap tmap_y_rem,
+                 const Shape g, const Ptrs a) {
   extern __shared__ uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) TRACE(0);
@@ -486,15 +616,14 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   uint8_t* hstage = smem + g.stages * g.slot_bytes;
   float* sbias_all = reinterpret_cast<float*>(hstage + 2 * g.hs_bytes);
   float* spart = sbias_all + kEpiWarps * (kBiasBytesPerWarp / 4);             // [2][128][kSpartPerRow]
-  uint32_t* s_words_all = reinterpret_cast<uint32_t*>(spart + 2 * kBlockM * kSpartPerRow);
-  unsigned int* s_hist = s_words_all + kEpiWarps * kRouteWordsPerWarp;        // [kMaxExperts]
+  uint32_t* s_words_all = reinterpret_cast<uint32_t*>(spart + 2 * kBlockM * kSpartPerRow);   // [16 warps][16]: tokens per warp x words
+  unsigned int* s_hist = s_words_all + kEpiWarps * 16;                        // [kMaxExperts]
   Barriers* bars = reinterpret_cast<Barriers*>(s_hist + kMaxExperts);
 
   const int rm = static_cast<int>(tc::cluster_ctarank());
   const int p = static_cast<int>(blockIdx.x) >> 1, P = static_cast<int>(gridDim.x) >> 1;
-  int* const ws_done = a.sync + kSyncHeaderInts;
-  int* const ws_ticket = ws_done + kMaxBlocks;
-  int* const ws_ready = ws_ticket + kMaxBlocks;
+  int* const ws_rec = a.sync + kSyncHeaderInts;                        // per block: [0] done, [1] ready
+  const int n_blocks = 2 * g.m_pairs;
 
   if (warp == 0 && lane == 0) {
     tc::prefetch_tensormap(&tmap_x);
@@ -515,7 +644,6 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     }
     tc::mbar_init(&bars->route_req, 1);
     tc::mbar_init(&bars->route_done, kEpiWarps);
-    tc::mbar_init(&bars->fin, 1);
     tc::fence_mbar_init();
   }
   if (warp == 2) {
@@ -523,6 +651,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     if (lane == 0) {
       tc::prefetch_tensormap(&tmap_hs);
       tc::prefetch_tensormap(&tmap_y);
+      tc::prefetch_tensormap(&tmap_hs_rem);
+      tc::prefetch_tensormap(&tmap_y_rem);
     }
   }
   for (int i = threadIdx.x; i < kMaxExperts; i += kNumThreads) s_hist[i] = 0u;
@@ -541,6 +671,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 
   if (warp == 0 || warp == 3) {
     // ================================================================== TMA producers (A: warp 0, B: warp 3)
+    // both operands of both CTAs complete on the leader's full[s]
     const bool do_a = warp == 0;
     int s = 0;
     uint32_t ph = 0;
@@ -550,11 +681,16 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       const int ks = phase == 0 ? g.ks1 : g.ks3;
       for (int it = 0; phase == 0 ? item1(g, it, p, P, rm, t) : item3(g, it, p, P, rm, t); ++it) {
         if (phase == 1 && do_a) {
-          // the block's H rows are complete and masked once every routing chunk of the block has been counted
+          // the block's H rows are complete and routed once every routing chunk of the block has been counted
           if (lane == 0) {
-            const int* flag = ws_ready + t.m_blk;
-            while (ld_acquire(flag) < g.chunks_per_block) {
-            }
+#if MOE_TRACE
+            if (it == 0) TRACE(62);
+#endif
+            const int* flag = ws_rec + t.m_blk * kBlockRecInts + 1;
+            while (ld_acquire(flag) < g.chunks_per_block) __nanosleep(40);
+#if MOE_TRACE
+            if (it == 0) TRACE(63);
+#endif
           }
           __syncwarp();
           fence_proxy_async_all();   // generic-proxy writes of other SMs (acquired above) -> this thread's TMA reads
@@ -565,15 +701,20 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           uint8_t* sb = sa + ks * kABytes;
           if (tc::elect_one()) {
             const uint32_t full_leader = full_leader0 + static_cast<uint32_t>(s) * 8u;
-            if (do_a) {
-              if (rm == 0) tc::mbar_arrive_expect_tx(&bars->full[s], 2u * (phase == 0 ? bytes1 : bytes3));
-              tc::tma_load_3d_2sm(sa, phase == 0 ? &tmap_x : &tmap_hl, full_leader, 0, t.m_blk * kBlockM, kb);
+            if (phase == 0) {
+              if (do_a) {
+                if (rm == 0) tc::mbar_arrive_expect_tx(&bars->full[s], 2u * bytes1);
+                tc::tma_load_3d_2sm(sa, &tmap_x, full_leader, 0, t.m_blk * kBlockM, kb);
 #if MOE_TRACE
-              if (phase == 0 && it == 0 && kb == 0) TRACE(7);
+                if (it == 0 && kb == 0) TRACE(7);
 #endif
-            } else if (phase == 0) {
-              // CTA 0 of the pair stages the value rows, CTA 1 the gate rows of the tile's neurons
-              tc::tma_load_3d_2sm(sb, &tmap_w1, full_leader, 0, (rm == 0 ? 0 : g.h) + t.n * g.nv, kb);
+              } else {
+                // CTA 0 of the pair stages the value rows, CTA 1 the gate rows of the tile's neurons
+                tc::tma_load_3d_2sm(sb, &tmap_w1, full_leader, 0, (rm == 0 ? 0 : g.h) + t.n * g.nv, kb);
+              }
+            } else if (do_a) {
+              if (rm == 0) tc::mbar_arrive_expect_tx(&bars->full[s], 2u * bytes3);
+              tc::tma_load_3d_2sm(sa, &tmap_hl, full_leader, 0, t.m_blk * kBlockM, kb);
             } else {
               tc::tma_load_3d_2sm(sb, &tmap_w2, full_leader, 0, t.n * g.bn + rm * (g.bn / 2), kb);
             }
@@ -648,48 +789,56 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       int use[2] = {0, 0};        // completed uses of each staging buffer
       int st_it = 0;              // staged phase-1 tiles so far
       uint32_t r_posted = 0;
-      auto claim_and_route = [&](int m_blk) {
-        for (;;) {
-          const int c = atomicAdd(ws_ticket + m_blk, 1);
-          if (c >= g.chunks_per_block) break;
-          bars->req_block = m_blk;
-          bars->req_chunk = c;
-          tc::mbar_arrive(&bars->route_req);
-          tc::mbar_wait(&bars->route_done, r_posted & 1u);
-          ++r_posted;
-          __threadfence();
-          atomicAdd(ws_ready + m_blk, 1);
-        }
-      };
       Item t;
       for (int it = 0; item1(g, it, p, P, rm, t); ++it, ++st_it) {
         const int buf = st_it & 1;
         tc::mbar_wait(&bars->hs_full[buf], use[buf] & 1u);
-        tc::tma_store_2d(&tmap_hs, hstage + buf * g.hs_bytes, t.n * g.nv, t.m_blk * kBlockM);   // rows beyond T are clipped
+        {   // one store per panel of the staging layout; rows beyond T are clipped
+          const uint8_t* src = hstage + buf * g.hs_bytes;
+          const int n_full = g.nv >> 6;
+          for (int pn = 0; pn < n_full; ++pn)
+            tc::tma_store_2d(&tmap_hs, src + pn * (kBlockM * 128), t.n * g.nv + 64 * pn, t.m_blk * kBlockM);
+          if (g.nv & 63) tc::tma_store_2d(&tmap_hs_rem, src + n_full * (kBlockM * 128), t.n * g.nv + 64 * n_full, t.m_blk * kBlockM);
+        }
         tc::tma_store_commit();
         tc::tma_store_wait<0>();          // H tile globally written (not only read out of smem)
         tc::mbar_arrive(&bars->hs_empty[buf]);
         ++use[buf];
         fence_proxy_async_all();
         __threadfence();                  // H tile + the tile's scores (ordered by hs_full) before the count
-        const int prev = atomicAdd(ws_done + t.m_blk, 1);
-        if (prev == g.n_tiles1 - 1) {
-          __threadfence();                // acquire: the other CTAs' tiles of this block happen-before the routing
-          claim_and_route(t.m_blk);
-        }
+        atomicAdd(ws_rec + t.m_blk * kBlockRecInts, 1);
+#if MOE_TRACE
+        if (st_it < 13) TRACE(8 + 4 * st_it + 3);
+#endif
       }
+      const int consumers = g.n_tiles3 * g.split3;      // phase-3 items per row block
       for (int it = 0; item3(g, it, p, P, rm, t); ++it) {
-        // make sure the block gets routed even if the CTA that completed it is busy: wait for its last
-        // phase-1 tile, then take whatever chunks are still unclaimed
+        // wait until every phase-1 tile of the block is published, then route this item's share of the block:
+        // consumer r of the block's `consumers` items takes chunks r, r + consumers, ...
         {
-          const int* flag = ws_done + t.m_blk;
-          while (ld_acquire(flag) < g.n_tiles1) {
-          }
+          const int* flag = ws_rec + t.m_blk * kBlockRecInts;
+          while (ld_acquire(flag) < g.n_tiles1) __nanosleep(40);
         }
-        claim_and_route(t.m_blk);
+        // the epilogue warps route this item's chunks (same formula there); count them for the block's consumers
+        tc::mbar_arrive(&bars->route_req);
+        tc::mbar_wait(&bars->route_done, r_posted & 1u);
+        ++r_posted;
+        int mine = 0;
+        for (int c = t.n * g.split3 + t.slice; c < g.chunks_per_block; c += consumers) ++mine;
+        if (mine > 0) {
+          __threadfence();
+          atomicAdd(ws_rec + t.m_blk * kBlockRecInts + 1, mine);
+        }
         if (g.split3 == 1) {
           tc::mbar_wait(&bars->hs_full[0], use[0] & 1u);
-          tc::tma_store_2d(&tmap_y, hstage, t.n * g.bn, t.m_blk * kBlockM);   // clipped at T rows / d columns
+          {   // clipped at T rows / d columns
+            const int n_full = g.bn >> 6;
+            for (int pn = 0; pn < n_full; ++pn)
+              if (t.n * g.bn + 64 * pn < g.d)
+                tc::tma_store_2d(&tmap_y, hstage + pn * (kBlockM * 128), t.n * g.bn + 64 * pn, t.m_blk * kBlockM);
+            if ((g.bn & 63) && t.n * g.bn + 64 * n_full < g.d)
+              tc::tma_store_2d(&tmap_y_rem, hstage + n_full * (kBlockM * 128), t.n * g.bn + 64 * n_full, t.m_blk * kBlockM);
+          }
           tc::tma_store_commit();
           tc::tma_store_wait_read<0>();
           tc::mbar_arrive(&bars->hs_empty[0]);
@@ -697,7 +846,6 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         }
       }
       tc::tma_store_wait<0>();
-      tc::mbar_arrive(&bars->fin);
     }
     __syncwarp();
   } else {
@@ -706,58 +854,66 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     const int q = warp & 3;            // TMEM lane quarter this warp may access
     const int cg = ew >> 2;            // column group 0..3
     float* sbias = sbias_all + ew * (kBiasBytesPerWarp / 4);
-    uint32_t* s_words = s_words_all + ew * kRouteWordsPerWarp;
+    uint32_t* s_words = s_words_all + ew * 16;
     const int q_row = 32 * q + lane;
-    uint32_t seen = 0;                 // routing requests served
-
-    auto serve = [&]() {
-      const int m_blk = bars->req_block, c = bars->req_chunk;
-      route_chunk(g, a, m_blk * kBlockM + c * (kEpiThreads >> g.tpt_log2), min(g.T, (m_blk + 1) * kBlockM), ew, lane, s_words,
-                  s_hist);
-      ++seen;
-      __threadfence();     // zero-writes / labels visible device-wide before the sync warp counts the chunk
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&bars->route_done);
-    };
-    // wait on one of this CTA's barriers, serving routing requests meanwhile (a request posted by our own sync
-    // warp may be what the awaited event transitively depends on)
-    auto wait_or_serve = [&](uint64_t* bar, uint32_t parity) {
-      for (;;) {
-        if (__all_sync(0xffffffffu, tc::mbar_try_wait(bar, parity))) break;
-        if (__all_sync(0xffffffffu, tc::mbar_try_wait(&bars->route_req, seen & 1u))) serve();
-      }
-    };
-
     int acc_it = 0;
     int use[2] = {0, 0};
     Item t;
+    const StageLayout hl1 = stage_layout(g.nv), hl3 = stage_layout(g.bn);
     // ---------------------------------------------------------------- phase 1
     {
       const int cpg = g.nv / 4;
       const int col0 = cg * cpg;
+      // bias slices: the first tile's are staged up front, every later tile's are fetched into registers while
+      // the previous tile is being processed (a staged load per tile exposed ~0.8 us of global latency each time)
+      if (item1(g, 0, p, P, rm, t))
+        stage_bias(sbias, a.b1 != nullptr ? a.b1 + t.n * g.nv + col0 : nullptr,
+                   a.b1 != nullptr ? a.b1 + g.h + t.n * g.nv + col0 : nullptr, cpg, lane);
       for (int it = 0; item1(g, it, p, P, rm, t); ++it, ++acc_it) {
         const int as = acc_it & 1;
         const int buf = it & 1;
-        const int n_tile0 = t.n * g.nv;
-        stage_bias(sbias, a.b1 != nullptr ? a.b1 + n_tile0 + col0 : nullptr,
-                   a.b1 != nullptr ? a.b1 + g.h + n_tile0 + col0 : nullptr, cpg, lane);
-        if (use[buf] > 0) wait_or_serve(&bars->hs_empty[buf], (use[buf] - 1) & 1u);   // staging buffer drained
-        wait_or_serve(&bars->tmem_full[as], (acc_it >> 1) & 1u);
+        float nb[4] = {0.f, 0.f, 0.f, 0.f};
+        Item tn;
+        const bool has_next = item1(g, it + 1, p, P, rm, tn);
+        if (has_next && a.b1 != nullptr) {
+          const float* bv = a.b1 + tn.n * g.nv + col0;
+          const float* bg = bv + g.h;
+          if (lane < cpg) {
+            nb[0] = __ldg(bv + lane);
+            nb[2] = __ldg(bg + lane);
+          }
+          if (lane + 32 < cpg) {
+            nb[1] = __ldg(bv + lane + 32);
+            nb[3] = __ldg(bg + lane + 32);
+          }
+        }
+        if (use[buf] > 0) tc::mbar_wait(&bars->hs_empty[buf], (use[buf] - 1) & 1u);   // staging buffer drained
+        tc::mbar_wait(&bars->tmem_full[as], (acc_it >> 1) & 1u);
         tc::fence_after_thread_sync();
 #if MOE_TRACE
         if (ew == 0 && lane == 0 && acc_it < 13) TRACE(8 + 4 * acc_it + 1);
 #endif
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + as * kAccStride;
-        __nv_bfloat16* hrow = reinterpret_cast<__nv_bfloat16*>(hstage + buf * g.hs_bytes) + q_row * g.nv;
+        const uint32_t hbase = tc::smem_u32(hstage + buf * g.hs_bytes);
         float* spart_row = spart + (buf * kBlockM + q_row) * kSpartPerRow;
         if (g.act == MOE_ACT_GELU)
-          geglu_group<CH, MOE_ACT_GELU>(g, taddr, sbias, hrow, spart_row, col0, cpg, cg);
+          geglu_group<CH, MOE_ACT_GELU>(g, taddr, sbias, hbase, hl1, q_row, spart_row, col0, cpg, cg);
+#if MOE_TRACE
+        else if (g.act == 2)
+          geglu_group<CH, 2>(g, taddr, sbias, hbase, hl1, q_row, spart_row, col0, cpg, cg);
+#endif
         else
-          geglu_group<CH, MOE_ACT_RELU>(g, taddr, sbias, hrow, spart_row, col0, cpg, cg);
+          geglu_group<CH, MOE_ACT_RELU>(g, taddr, sbias, hbase, hl1, q_row, spart_row, col0, cpg, cg);
         // accumulator stage drained -> the leader's MMA thread may overwrite it
         tc::fence_before_thread_sync();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive_cluster(tc::mapa_u32(&bars->tmem_empty[as], 0));
+        if (has_next) {   // this warp is done reading the current slices
+          sbias[lane] = nb[0];
+          sbias[lane + 32] = nb[1];
+          sbias[64 + lane] = nb[2];
+          sbias[64 + lane + 32] = nb[3];
+        }
         // expert scores of this row: the 4 column-group warps of the lane quarter meet, the first one writes
         tc::named_bar_sync(2 + q, 4 * 32);
         if (cg == 0) {
@@ -791,15 +947,30 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       const int col0 = cg * cpg;
       for (int it = 0; item3(g, it, p, P, rm, t); ++it, ++acc_it) {
         const int as = acc_it & 1;
+        // ---- routing role: once the sync warp has seen every phase-1 tile of the block, route this item's share
+        // of the block's chunks (consumer r of the block's items takes chunks r, r + consumers, ...)
+        tc::mbar_wait(&bars->route_req, it & 1u);
+#if MOE_TRACE
+        if (ew == 0 && lane == 0 && it == 0) TRACE(60);
+#endif
+        for (int c = t.n * g.split3 + t.slice; c < g.chunks_per_block; c += g.n_tiles3 * g.split3)
+          route_dispatch(g, a, t.m_blk * kBlockM + c * g.chunk_tokens, min(g.T, (t.m_blk + 1) * kBlockM), ew, lane, s_words,
+                         s_hist);
+        __threadfence();     // labels / expert sets visible device-wide before the sync warp counts the chunks
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&bars->route_done);
+#if MOE_TRACE
+        if (ew == 0 && lane == 0) TRACE(61);
+#endif
         const int n0 = t.n * g.bn + col0;                  // first output column of this warp's group
         const int nvalid = max(0, min(cpg, g.d - n0));     // the last tile may overhang d
         stage_bias(sbias, a.b2 != nullptr ? a.b2 + n0 : nullptr, nullptr, nvalid, lane);
         if (g.split3 == 1) {
           // the whole staging area (both phase-1 buffers) holds one Y tile
-          if (use[0] > 0) wait_or_serve(&bars->hs_empty[0], (use[0] - 1) & 1u);
-          if (use[1] > 0) wait_or_serve(&bars->hs_empty[1], (use[1] - 1) & 1u);
+          if (use[0] > 0) tc::mbar_wait(&bars->hs_empty[0], (use[0] - 1) & 1u);
+          if (use[1] > 0) tc::mbar_wait(&bars->hs_empty[1], (use[1] - 1) & 1u);
         }
-        wait_or_serve(&bars->tmem_full[as], (acc_it >> 1) & 1u);
+        tc::mbar_wait(&bars->tmem_full[as], (acc_it >> 1) & 1u);
         tc::fence_after_thread_sync();
 #if MOE_TRACE
         if (ew == 0 && lane == 0 && acc_it < 13) TRACE(8 + 4 * acc_it + 1);
@@ -808,7 +979,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         const int row = t.m_blk * kBlockM + q_row;
         const bool row_ok = row < g.T;
         if (g.split3 == 1) {
-          __nv_bfloat16* yrow = reinterpret_cast<__nv_bfloat16*>(hstage) + q_row * g.bn + col0;
+          const uint32_t ybase = tc::smem_u32(hstage);
           for (int c = 0; c < cpg; c += CH) {
             uint32_t acc[CH];
             tc::tmem_ld_cols<CH>(taddr + c, acc);
@@ -820,7 +991,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
               yw[i / 2] = pack_bf16x2(__uint_as_float(acc[i]) + b.x, __uint_as_float(acc[i + 1]) + b.y);
               yw[i / 2 + 1] = pack_bf16x2(__uint_as_float(acc[i + 2]) + b.z, __uint_as_float(acc[i + 3]) + b.w);
             }
-            store_words<CH / 2>(yrow + c, yw);
+            stage_store<CH / 2>(ybase, hl3, q_row, col0 + c, yw);
           }
           tc::fence_before_thread_sync();
           __syncwarp();
@@ -894,8 +1065,6 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 #endif
       }
     }
-    // stay available for routing requests until the sync warp has nothing more to post
-    wait_or_serve(&bars->fin, 0u);
 #if MOE_TRACE
     if (ew == 0 && lane == 0) TRACE(4);
 #endif
@@ -917,12 +1086,10 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   tc::cluster_sync_all();   // nobody exits while the peer may still signal its smem (also a CTA barrier)
   tc::fence_after_thread_sync();
   if (bars->last_cta) {
-    // every other CTA is past its last access: leave the sync arrays clean for the next launch
-    const int n_blocks = 2 * g.m_pairs;
+    // every other CTA is past its last access: leave the sync area clean for the next launch
     for (int i = threadIdx.x; i < n_blocks; i += kNumThreads) {
-      ws_done[i] = 0;
-      ws_ticket[i] = 0;
-      ws_ready[i] = 0;
+      ws_rec[i * kBlockRecInts] = 0;
+      ws_rec[i * kBlockRecInts + 1] = 0;
     }
     if (threadIdx.x == 0) a.sync[0] = 0;
   }
@@ -987,7 +1154,8 @@ int moe_ffn_fused(const void* x, const void* w1p, const float* b1p, const void* 
   MOE_REQUIRE(T >= 0 && d >= 8 && h >= 8 && E >= 1 && es >= 1 && k >= 0 && k <= E, MOE_ERR_INVALID_ARGUMENT,
               "moe_ffn_fused: bad sizes T=%d d=%d h=%d E=%d es=%d k=%d", T, d, h, E, es, k);
   MOE_REQUIRE(static_cast<long long>(E) * es == h, MOE_ERR_INVALID_ARGUMENT, "moe_ffn_fused: E*es=%d*%d != h=%d", E, es, h);
-  MOE_REQUIRE(act == MOE_ACT_GELU || act == MOE_ACT_RELU, MOE_ERR_INVALID_ARGUMENT, "moe_ffn_fused: act=%d", act);
+  MOE_REQUIRE(act == MOE_ACT_GELU || act == MOE_ACT_RELU || (MOE_TRACE && act == 2), MOE_ERR_INVALID_ARGUMENT,
+              "moe_ffn_fused: act=%d", act);
   MOE_REQUIRE(d % 64 == 0 && h % 64 == 0, MOE_ERR_UNSUPPORTED_SHAPE,
               "moe_ffn_fused: d=%d and h=%d must be multiples of 64 (use the unfused kernels)", d, h);
   MOE_REQUIRE(es % 4 == 0 && E <= kMaxExperts && h < 65536, MOE_ERR_UNSUPPORTED_SHAPE,
@@ -1103,7 +1271,8 @@ int moe_ffn_fused(const void* x, const void* w1p, const float* b1p, const void* 
   // ---- pipeline: k-blocks per stage (2 if at least 3 stages fit), ring slot = the larger of the two phases
   g.hs_bytes = kBlockM * nv * 2;
   const int fixed = 1024 + 2 * g.hs_bytes + kEpiWarps * kBiasBytesPerWarp + 2 * kBlockM * kSpartPerRow * 4 +
-                    kEpiWarps * kRouteWordsPerWarp * 4 + kMaxExperts * 4 + static_cast<int>(sizeof(Barriers)) + 64;
+                    kEpiWarps * 16 * 4 + kMaxExperts * 4 +
+                    static_cast<int>(sizeof(Barriers)) + 64;
   int ks = 2;
   if (const char* e = getenv("MOE_FUSED_KS")) ks = atoi(e) == 1 ? 1 : 2;
   for (; ks >= 1; --ks) {
@@ -1123,14 +1292,32 @@ int moe_ffn_fused(const void* x, const void* w1p, const float* b1p, const void* 
   while (g.split3 > 1 && (g.split3 - 1) * g.kb_per_slice3 >= g.nkb3) --g.split3;
   g.items3 = g.m_pairs * g.n_tiles3 * g.split3;
 
-  // ---- routing geometry: 16 experts per thread, tpt (a power of two) threads per token
-  int tpt = 1;
-  while (tpt * kKeys < E) tpt <<= 1;
-  MOE_REQUIRE(tpt <= 32, MOE_ERR_UNSUPPORTED_SHAPE, "moe_ffn_fused: E=%d too large", E);
-  g.tpt = tpt;
-  g.tpt_log2 = ilog2(tpt);
-  g.chunks_per_block = kBlockM / (kEpiThreads / tpt) > 0 ? kBlockM / (kEpiThreads / tpt) : 1;
-  MOE_REQUIRE(((E + 31) / 32) * (32 / tpt) <= kRouteWordsPerWarp, MOE_ERR_UNSUPPORTED_SHAPE, "moe_ffn_fused: E=%d", E);
+  // ---- routing geometry: L lanes per token (chunk = 512 / L tokens, L / 4 chunks per 128-row block).  The
+  // block's `consumers` phase-3 items share its chunks, so few consumers want large chunks; each lane holds
+  // kpt = ceil(E / L) <= 16 experts.
+  {
+    const int consumers = g.n_tiles3 * g.split3;
+    // a consumer waits only for items with a smaller index (acyclic) as long as one round covers a block
+    MOE_REQUIRE(consumers <= P, MOE_ERR_UNSUPPORTED_SHAPE, "moe_ffn_fused: %d down-projection items per row block > %d CTA pairs",
+                consumers, P);
+    // measured (profiles/r01_fused_lanes_sweep.log): 64-token chunks for the two-consumer d = 320 shape, otherwise
+    // one token per warp (32 lanes), which spreads a block over as many consumers as possible
+    int L = consumers >= 4 ? 32 : (consumers >= 2 ? 8 : 4);
+    while (L < 32 && (E + L - 1) / L > 16) L <<= 1;
+    if (const char* e = getenv("MOE_FUSED_LANES")) {
+      const int v = atoi(e);
+      if ((v == 4 || v == 8 || v == 16 || v == 32) && (E + v - 1) / v <= 16) L = v;
+    }
+    int kpt = 1;
+    while (kpt * L < E) kpt <<= 1;
+    MOE_REQUIRE(kpt <= 16, MOE_ERR_UNSUPPORTED_SHAPE, "moe_ffn_fused: E=%d too large", E);
+    g.lanes = L;
+    g.lanes_log2 = ilog2(L);
+    g.kpt = kpt;
+    g.chunk_tokens = kEpiThreads / L;
+    g.chunks_per_block = kBlockM / g.chunk_tokens;
+    g.words = (E + 31) / 32;
+  }
   g.act = act;
   g.mask_h = mask_h;
   g.count_begin = count_begin;
@@ -1140,22 +1327,34 @@ int moe_ffn_fused(const void* x, const void* w1p, const float* b1p, const void* 
   if (getenv("MOE_DEBUG_PRINT"))
     fprintf(stderr,
             "[moe_ffn_fused] T=%d d=%d h=%d E=%d es=%d k=%d | nv=%d tiles1=%d ks1=%d | bn=%d tiles3=%d split=%d ks3=%d kb/slice=%d | "
-            "stages=%d slot=%d | tpt=%d chunks/block=%d | items %d + %d on %d pairs\n",
+            "stages=%d slot=%d | route lanes=%d kpt=%d chunks/block=%d | items %d + %d on %d pairs\n",
             T, d, h, E, es, k, g.nv, g.n_tiles1, g.ks1, g.bn, g.n_tiles3, g.split3, g.ks3, g.kb_per_slice3, g.stages,
-            g.slot_bytes, g.tpt, g.chunks_per_block, g.items1, g.items3, P);
+            g.slot_bytes, g.lanes, g.kpt, g.chunks_per_block, g.items1, g.items3, P);
 
-  CUtensorMap tx, tw1, ths, thl, tw2, ty;
+  CUtensorMap tx, tw1, ths, thl, tw2, ty, ths_rem, ty_rem;
   int rc;
   if ((rc = make_tmap_bf16_kblocks(&tx, x, static_cast<uint64_t>(T), static_cast<uint64_t>(d), kBlockM, static_cast<uint32_t>(g.ks1)))) return rc;
   if ((rc = make_tmap_bf16_kblocks(&tw1, w1p, static_cast<uint64_t>(2) * h, static_cast<uint64_t>(d), static_cast<uint32_t>(nv),
                                    static_cast<uint32_t>(g.ks1))))
     return rc;
-  if ((rc = make_tmap_bf16_2d(&ths, H, static_cast<uint64_t>(T), static_cast<uint64_t>(h), kBlockM, static_cast<uint32_t>(nv), false))) return rc;
+  // staging-tile stores: 64-column panels with the 128-byte swizzle + a remainder panel (see StageLayout)
+  auto rem_swizzle = [](int cols) { return cols == 32 ? 64 : (cols == 16 ? 32 : 0); };
+  if ((rc = make_tmap_bf16_2d_sw(&ths, H, static_cast<uint64_t>(T), static_cast<uint64_t>(h), kBlockM, nv >= 64 ? 64u : static_cast<uint32_t>(nv),
+                                 nv >= 64 ? 128 : rem_swizzle(nv))))
+    return rc;
+  if ((rc = make_tmap_bf16_2d_sw(&ths_rem, H, static_cast<uint64_t>(T), static_cast<uint64_t>(h), kBlockM,
+                                 (nv & 63) ? static_cast<uint32_t>(nv & 63) : 64u, (nv & 63) ? rem_swizzle(nv & 63) : 128)))
+    return rc;
   if ((rc = make_tmap_bf16_kblocks(&thl, H, static_cast<uint64_t>(T), static_cast<uint64_t>(h), kBlockM, static_cast<uint32_t>(g.ks3)))) return rc;
   if ((rc = make_tmap_bf16_kblocks(&tw2, w2p, static_cast<uint64_t>(d), static_cast<uint64_t>(h), static_cast<uint32_t>(g.bn / 2),
                                    static_cast<uint32_t>(g.ks3))))
     return rc;
-  if ((rc = make_tmap_bf16_2d(&ty, Y, static_cast<uint64_t>(T), static_cast<uint64_t>(d), kBlockM, static_cast<uint32_t>(g.bn), false))) return rc;
+  if ((rc = make_tmap_bf16_2d_sw(&ty, Y, static_cast<uint64_t>(T), static_cast<uint64_t>(d), kBlockM, g.bn >= 64 ? 64u : static_cast<uint32_t>(g.bn),
+                                 g.bn >= 64 ? 128 : rem_swizzle(g.bn))))
+    return rc;
+  if ((rc = make_tmap_bf16_2d_sw(&ty_rem, Y, static_cast<uint64_t>(T), static_cast<uint64_t>(d), kBlockM,
+                                 (g.bn & 63) ? static_cast<uint32_t>(g.bn & 63) : 64u, (g.bn & 63) ? rem_swizzle(g.bn & 63) : 128)))
+    return rc;
 
   Ptrs a = {};
   a.b1 = b1p;
@@ -1193,7 +1392,7 @@ int moe_ffn_fused(const void* x, const void* w1p, const float* b1p, const void* 
   do {                                                                                              \
     rc = ensure_smem(reinterpret_cast<const void*>(ffn_fused_kernel<CHV>));                         \
     if (rc) return rc;                                                                              \
-    le = cudaLaunchKernelEx(&cfg, ffn_fused_kernel<CHV>, tx, tw1, ths, thl, tw2, ty, g, a);         \
+    le = cudaLaunchKernelEx(&cfg, ffn_fused_kernel<CHV>, tx, tw1, ths, thl, tw2, ty, ths_rem, ty_rem, g, a); \
   } while (0)
   switch (ch1) {
     case 32: MOE_LAUNCH_FUSED(32); break;

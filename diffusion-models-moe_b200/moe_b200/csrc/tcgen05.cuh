@@ -376,6 +376,9 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // the 128-byte swizzle.  Uses the driver entry point through the runtime (no -lcuda needed).
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
                       uint32_t box_cols, bool swizzle128 = true);
+// same with the shared-memory swizzle span given in bytes (0 = none, 32, 64 or 128; box_cols * 2 <= span)
+int make_tmap_bf16_2d_sw(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                         uint32_t box_cols, int swizzle_bytes);
 // [cols/64][rows][64] view of a row-major bf16 [rows, cols] matrix (cols % 64 == 0), box {64, box_rows, box_kblocks},
 // 128-byte swizzle: one box = box_kblocks consecutive [box_rows x 64] swizzled k-block tiles.
 int make_tmap_bf16_kblocks(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,

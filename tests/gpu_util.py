@@ -54,7 +54,7 @@ def cuda_layer(layer, ratio, act=O.ACT_GELU, removed=None, flags=None, want_gate
                 y=y.float().cpu().view(*lead, -1), k=k, E=E, es=es, sets=bits_to_sets(bits, E))
 
 
-def fused_layer(layer, ratio, act=O.ACT_GELU, removed=None, count_rows=None, repeats=1):
+def fused_layer(layer, ratio, act=O.ACT_GELU, removed=None, count_rows=None, repeats=1, mask_h=True):
     """The same layer through ONE moe_ffn_fused launch (K1 -> routing -> K3 in a persistent kernel)."""
     lay = ExpertLayout.from_labels(layer["labels"])
     E, es = lay.n_experts, lay.expert_size
@@ -68,7 +68,7 @@ def fused_layer(layer, ratio, act=O.ACT_GELU, removed=None, count_rows=None, rep
     for _ in range(repeats):
         hist = torch.zeros(E, dtype=torch.int64, device=DEV)
         y, H, scores, bits, idx = M.ffn_fused(xt, p.w1p, p.b1p, p.w2p, p.b2, E, es, k, act, removed_bits=rb,
-                                              want_bits=True, want_idx=True, hist=hist, count_rows=rows)
+                                              want_bits=True, want_idx=True, hist=hist, count_rows=rows, mask_h=mask_h)
     torch.cuda.synchronize()
     inv = lay.inv_perm
     return dict(H=H.float().cpu()[:, inv].view(*lead, -1), scores=scores.cpu(), idx=idx.cpu().long(), bits=bits.cpu(),

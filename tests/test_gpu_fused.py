@@ -100,7 +100,23 @@ def test_fused_repeat_launches_share_workspace(lib):
         assert torch.equal(x["hist"], y["hist"])
     ws = M.fused_workspace(DEV, 1)
     torch.cuda.synchronize()
-    assert int(ws[: 4 * (16 + 3 * 16384)].view(torch.int32).abs().sum()) == 0
+    sync_bytes = 4 * (32 + 2048 * 32)      # header + per-block records
+    assert int(ws[:sync_bytes].view(torch.int32).abs().sum()) == 0
+
+
+def test_fused_without_masking_is_the_dense_ffn(lib):
+    """mask_h=False (the ExpertPredictivity contract, expert_activation.py:62: statistics only, unmasked output): the
+    routing outputs are unchanged, H and Y are those of the dense FFN."""
+    for d, h, shape, es in [(320, 1280, (2, 777), 20), (1280, 5120, (2, 64), 20), (320, 1280, (1, 500), 64)]:
+        layer = O.synthetic_layer(d, h, shape, es, seed=11)
+        a = fused_layer(layer, 0.3, mask_h=True)
+        b = fused_layer(layer, 0.3, mask_h=False)
+        assert torch.equal(a["idx"], b["idx"]) and torch.equal(a["hist"], b["hist"]) and torch.equal(a["bits"], b["bits"])
+        assert torch.equal(a["scores"], b["scores"])
+        dense = cuda_layer(layer, 1.0)                            # k == E: identity mask through the separate kernels
+        assert rel_err(b["H"], dense["H_unmasked"]) < 1e-6
+        assert rel_err(b["y"], dense["y"]) < 2e-3
+        assert (a["H"] == 0).float().mean() > 0.6                 # ~70 % of the neurons masked at ratio 0.3
 
 
 def test_fused_unsupported_geometry_raises(lib):

@@ -1,0 +1,72 @@
+"""In-kernel timeline of the fused layer kernel.  Needs the trace build:
+    MOE_LIB_VARIANT=trace python diffusion-models-moe_b200/moe_b200/build.py
+    MOE_LIB_VARIANT=trace python tools/trace_fused.py [d T]..."""
+import ctypes, os, sys
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "diffusion-models-moe_b200"))
+os.environ.setdefault("MOE_LIB_VARIANT", "trace")
+import moe_b200 as M
+from moe_b200 import _lib
+dev = "cuda:0"
+lib = _lib.load()
+ES = int(os.environ.get("ES", "20"))
+
+
+def trace():
+    buf = (ctypes.c_ulonglong * (256 * 64))()
+    assert lib.moe_debug_trace_fused(buf, 256 * 64) == 0, lib.moe_last_error()
+    return torch.tensor(list(buf), dtype=torch.int64).view(256, 64)
+
+
+def show(name, tr, ms):
+    tr = tr[tr[:, 0] > 0]
+    t0 = tr[:, 0].min()
+    rel = (tr - t0).double() / 1e3
+    rel[tr == 0] = float("nan")
+
+    def col(i):
+        c = rel[:, i]; c = c[~torch.isnan(c)]
+        return f"{c.min():6.2f}/{c.median():6.2f}/{c.max():6.2f} ({len(c):3d})" if len(c) else "     -"
+    print(f"{name}: {ms*1e3:7.1f}us event-timed, {tr.shape[0]} CTAs; min/median/max over CTAs (n), us since first CTA entry")
+    print(f"   entry {col(0)} | setup {col(1)} | pdl_wait {col(2)} | first TMA {col(7)} | first MMA {col(3)}")
+    for it in range(8):
+        b = 8 + 4 * it
+        if torch.isnan(rel[:, b]).all() and torch.isnan(rel[:, b + 1]).all():
+            break
+        print(f"   item {it:2d}: mma-commit {col(b)} | epi-begin {col(b+1)} | epi-done {col(b+2)} | stored+signalled {col(b+3)}")
+    print(f"   route: first begin {col(60)} | last end {col(61)} | K3 A-producer: ready-wait begin {col(62)} end {col(63)}")
+    print(f"   K3 stage 1 detail: a_full {col(44)} | mask loop done {col(52)} | fence done {col(53)} | arrived {col(45)}")
+    for i in range(3):
+        print(f"   K3 stage {i}: masker a_full {col(40+4*i)} | masker arrived {col(41+4*i)} | MMA masked-wait passed {col(42+4*i)} | MMA issued+commit {col(43+4*i)}")
+    def d(i, j):
+        c = rel[:, j] - rel[:, i]; c = c[~torch.isnan(c)]
+        return f"{c.min():5.2f}/{c.median():5.2f}/{c.max():5.2f}" if len(c) else "-"
+    print(f"   routing (last chunk of each CTA): whole item {d(60,61)} | select {d(56,57)} | labels/hist {d(57,58)} | "
+          f"zero-writes {d(58,59)} | 59->end {d(59,61)}")
+    print(f"   epi all done {col(4)} | teardown sync {col(5)} | exit {col(6)}")
+
+
+shapes = [(320, 8192), (640, 2048), (1280, 512), (1280, 128)]
+if len(sys.argv) > 2:
+    shapes = [(int(sys.argv[i]), int(sys.argv[i + 1])) for i in range(1, len(sys.argv) - 1, 2)]
+for d, T in shapes:
+    h = 4 * d; E = h // ES; k = int(E * 0.3)
+    gen = torch.Generator().manual_seed(0)
+    x = torch.randn(T, d, generator=gen).to(dev, torch.bfloat16)
+    w1 = (torch.randn(2 * h, d, generator=gen) / d ** 0.5).to(dev, torch.bfloat16)
+    b1 = torch.zeros(2 * h, device=dev)
+    w2 = (torch.randn(d, h, generator=gen) / h ** 0.5).to(dev, torch.bfloat16)
+    b2 = torch.zeros(d, device=dev)
+    H = torch.empty(T, h, dtype=torch.bfloat16, device=dev); sc = torch.empty(T, E, device=dev)
+    y = torch.empty(T, d, dtype=torch.bfloat16, device=dev)
+    hist = torch.zeros(E, dtype=torch.int64, device=dev)
+    fn = lambda: M.ffn_fused(x, w1, b1, w2, b2, E, ES, k, int(os.environ.get("ACT", "0")), hist=hist, count_rows=(0, T // 2), H_out=H, scores_out=sc, out=y, mask_h=bool(int(os.environ.get("MASK_H", "1"))))
+    print(f"==== d={d} T={T} es={ES}")
+    for _ in range(200):
+        fn()
+    torch.cuda.synchronize()
+    trace()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+    show("fused", trace(), e0.elapsed_time(e1))
