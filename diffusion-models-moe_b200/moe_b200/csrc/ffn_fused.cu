@@ -22,8 +22,8 @@
 // the landed H tiles in shared memory inside the phase-3 pipeline was tried and measured: the extra
 // wait / fence / cluster-arrive per stage cost ~1 us per stage, three times the main loop itself.)
 // All CTAs are co-resident (grid <= SM count, 1 CTA / SM) and every CTA finishes its phase-1 tiles, which
-// never wait on another CTA, before it waits for anything, so the waits cannot deadlock.  The last CTA to
-// exit zeroes the sync area again (the workspace must be zero before the first launch).
+// never wait on another CTA, before it waits for anything, so the waits cannot deadlock.  The last consumer of a
+// block zeroes its record again (the workspace must be zero before the first launch).
 //
 // Warp roles (640 threads):
 //   warp 0      A-tile TMA producer (x in phase 1, H in phase 3 -- waits for ready[m])
@@ -59,7 +59,7 @@ constexpr int kBiasBytesPerWarp = 128 * 4;          // 2 x 64 floats
 constexpr int kSpartPerRow = 8;                      // partial / per-expert score slots per token row and tile
 constexpr int kMaxWords = 8;                         // expert-set words per token (E <= 256)
 constexpr int kMaxExperts = 32 * kMaxWords;
-// sync area (ints): header {exit counter}, then one 128-byte record per 128-row block {done, ready} (separate
+// sync area (ints): header (unused), then one 128-byte record per 128-row block {done, ready, visits} (separate
 // cache lines: pollers of different blocks do not serialise on one L2 line)
 constexpr int kSyncHeaderInts = 32;
 constexpr int kBlockRecInts = 32;
@@ -106,7 +106,8 @@ struct Shape {
   // routing
   int lanes, lanes_log2;                        // lanes per token in the routing stage (4, 8 or 16)
   int kpt;                                      // experts per routing lane: ceil(E / lanes) rounded up to a power of two
-  int chunk_tokens, chunks_per_block;           // chunk = 512 / lanes tokens = one pass of the 16 epilogue warps
+  int route_warps;                              // epilogue warps that take part in routing a chunk (1..16)
+  int chunk_tokens, chunks_per_block;           // chunk = route_warps * 32 / lanes tokens = one pass of those warps
   int words;                                    // expert-set words per token
   int act, mask_h, count_begin, count_end;
   uint32_t es_magic;
@@ -199,6 +200,18 @@ __device__ __forceinline__ uint64_t activate2(float x0, float x1) {
 __device__ __forceinline__ uint32_t float_key(float s) {
   const uint32_t u = __float_as_uint(s);
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// Every phase-3 item touches its block's record twice (its sync warp after the done-poll and its ready-add, its
+// A-tile producer after the ready-wait); the last of these 2 x consumers visits zeroes the record, so the sync area
+// is clean again when the kernel ends -- off the critical path, unlike a last-CTA-out sweep at kernel exit.
+__device__ __forceinline__ void block_consumed(int* rec, int visits) {
+  const int prev = atomicAdd(rec + 2, 1);
+  if (prev == visits - 1) {
+    rec[0] = 0;
+    rec[1] = 0;
+    rec[2] = 0;
+  }
 }
 
 // ------------------------------------------------------------------------------------------ work list
@@ -482,6 +495,7 @@ __device__ __forceinline__ void route_chunk(const Shape& g, const Ptrs& a, int t
 
 __device__ __forceinline__ void route_dispatch(const Shape& g, const Ptrs& a, int tok0, int tok_end, int ew, int lane,
                                                uint32_t* s_words, unsigned int* s_hist) {
+  if (ew >= g.route_warps) return;   // small chunks (many consumers per block) use only the first warps
   switch (g.kpt) {
     case 16: route_chunk<16>(g, a, tok0, tok_end, ew, lane, s_words, s_hist); break;
     case 8: route_chunk<8>(g, a, tok0, tok_end, ew, lane, s_words, s_hist); break;
@@ -558,18 +572,28 @@ __device__ __forceinline__ void stage_store(uint32_t base, const StageLayout& l,
 
 template <int CH, int ACT>
 __device__ __forceinline__ void geglu_group(const Shape& g, uint32_t taddr, const float* sbias, uint32_t hbase,
-                                            const StageLayout& hl, int q_row, float* spart_row, int col0, int cpg,
-                                            int cg) {
+                                            const StageLayout& hl, int q_row, float* spart_row, float* score_dst,
+                                            int col0, int cpg, int cg) {
   uint64_t score2 = pk2(0.f, 0.f);
   int chunk_in_expert = 0, e_slot = (g.chunks_per_expert > 0) ? cg * (cpg / g.es) : cg;
+  // the chunk's TMEM loads are split in two: the second half is in flight while the first half is processed
+  // (TMEM reads run at ~16 B/clk per lane quarter -- a whole tile takes ~1300 cycles to read out)
+  constexpr int kA = (CH >= 8) ? (CH / 2) / 4 * 4 : CH;
   for (int c = 0; c < cpg; c += CH) {
     uint32_t v[CH], gt[CH];
-    tc::tmem_ld_cols<CH>(taddr + col0 + c, v);
-    tc::tmem_ld_cols<CH>(taddr + g.nv + col0 + c, gt);
+    tc::tmem_ld_cols<kA>(taddr + col0 + c, v);
+    tc::tmem_ld_cols<kA>(taddr + g.nv + col0 + c, gt);
     tc::tmem_ld_wait();
+    if constexpr (kA < CH) {
+      tc::tmem_ld_cols<CH - kA>(taddr + col0 + c + kA, v + kA);
+      tc::tmem_ld_cols<CH - kA>(taddr + g.nv + col0 + c + kA, gt + kA);
+    }
     uint32_t hw[CH / 2];
 #pragma unroll
     for (int i = 0; i < CH; i += 4) {
+      if constexpr (kA < CH) {
+        if (i == kA) tc::tmem_ld_wait();
+      }
       const float4 bv = *reinterpret_cast<const float4*>(sbias + c + i);
       const float4 bg = *reinterpret_cast<const float4*>(sbias + 64 + c + i);
       float ga, gb, gc, gd;
@@ -590,7 +614,10 @@ __device__ __forceinline__ void geglu_group(const Shape& g, uint32_t taddr, cons
     if (g.chunks_per_expert > 0 && ++chunk_in_expert == g.chunks_per_expert) {
       float s0, s1;
       unpk2(score2, s0, s1);
-      spart_row[e_slot++] = s0 + s1;
+      // whole expert inside this thread's column group: its score goes straight to global memory
+      // (score_dst = this row's slice of the tile's experts, or null beyond T)
+      if (score_dst != nullptr) score_dst[e_slot] = s0 + s1;
+      ++e_slot;
       score2 = pk2(0.f, 0.f);
       chunk_in_expert = 0;
     }
@@ -687,10 +714,11 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             if (it == 0) TRACE(62);
 #endif
             const int* flag = ws_rec + t.m_blk * kBlockRecInts + 1;
-            while (ld_acquire(flag) < g.chunks_per_block) __nanosleep(40);
+            while (ld_acquire(flag) < g.chunks_per_block) __nanosleep(32);
 #if MOE_TRACE
             if (it == 0) TRACE(63);
 #endif
+            block_consumed(ws_rec + t.m_blk * kBlockRecInts, 2 * g.n_tiles3 * g.split3);
           }
           __syncwarp();
           fence_proxy_async_all();   // generic-proxy writes of other SMs (acquired above) -> this thread's TMA reads
@@ -785,39 +813,92 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     }
   } else if (warp == 2) {
     // ================================================================== store / sync warp
-    if (lane == 0) {
-      int use[2] = {0, 0};        // completed uses of each staging buffer
-      int st_it = 0;              // staged phase-1 tiles so far
-      uint32_t r_posted = 0;
+    {
+      // ---- phase 1 (whole warp): per tile, lane 0 issues the panel stores, releases the staging buffer as soon as
+      // the stores have READ it, and then publishes the PREVIOUS tile (whose stores have fully completed by then:
+      // wait_group 1).  Expert scores are written by the epilogue threads themselves (no barrier among the epilogue
+      // warps, which therefore drift apart and overlap each other's TMEM reads and math); only experts that span
+      // column groups are combined here from shared-memory partial sums.
+      int st_it = 0;
+      int use_p1[2] = {0, 0};
+      int pending_blk = -1;
       Item t;
       for (int it = 0; item1(g, it, p, P, rm, t); ++it, ++st_it) {
         const int buf = st_it & 1;
-        tc::mbar_wait(&bars->hs_full[buf], use[buf] & 1u);
-        {   // one store per panel of the staging layout; rows beyond T are clipped
+        tc::mbar_wait(&bars->hs_full[buf], use_p1[buf] & 1u);
+        if (lane == 0) {
           const uint8_t* src = hstage + buf * g.hs_bytes;
           const int n_full = g.nv >> 6;
           for (int pn = 0; pn < n_full; ++pn)
             tc::tma_store_2d(&tmap_hs, src + pn * (kBlockM * 128), t.n * g.nv + 64 * pn, t.m_blk * kBlockM);
           if (g.nv & 63) tc::tma_store_2d(&tmap_hs_rem, src + n_full * (kBlockM * 128), t.n * g.nv + 64 * n_full, t.m_blk * kBlockM);
+          tc::tma_store_commit();
         }
-        tc::tma_store_commit();
-        tc::tma_store_wait<0>();          // H tile globally written (not only read out of smem)
-        tc::mbar_arrive(&bars->hs_empty[buf]);
-        ++use[buf];
-        fence_proxy_async_all();
-        __threadfence();                  // H tile + the tile's scores (ordered by hs_full) before the count
-        atomicAdd(ws_rec + t.m_blk * kBlockRecInts, 1);
+        // experts that span column groups (es > nv / 4): combine the groups' partial sums from shared memory
+        if (g.chunks_per_expert == 0) {
+          const float* sp = spart + buf * kBlockM * kSpartPerRow;
+          for (int r = lane; r < kBlockM; r += 32) {
+            const int row = t.m_blk * kBlockM + r;
+            if (row >= g.T) break;
+            float* dst = a.scores + static_cast<size_t>(row) * g.E + t.n * g.experts_per_tile;
+            const float* src = sp + r * kSpartPerRow;
+            for (int e = 0; e < g.experts_per_tile; ++e) {
+              float tot = 0.f;
+              for (int j = 0; j < g.span; ++j) tot += src[e * g.span + j];
+              dst[e] = tot;
+            }
+          }
+          __threadfence();
+        }
+        __syncwarp();
+        if (lane == 0) {
+          tc::tma_store_wait_read<0>();
+          tc::mbar_arrive(&bars->hs_empty[buf]);   // the epilogue warps may refill the buffer
+          if (pending_blk >= 0) {
+            tc::tma_store_wait<1>();        // every group but the one just committed is globally written
+            fence_proxy_async_all();
+            __threadfence();                // previous H tile + its scores before the count
+            atomicAdd(ws_rec + pending_blk * kBlockRecInts, 1);
 #if MOE_TRACE
-        if (st_it < 13) TRACE(8 + 4 * st_it + 3);
+            if (st_it - 1 < 13) TRACE(8 + 4 * (st_it - 1) + 3);
 #endif
+          }
+        }
+        pending_blk = t.m_blk;
+        ++use_p1[buf];
+        __syncwarp();
       }
+      if (pending_blk >= 0) {
+        // the last tile's scores were written by all lanes: order them before lane 0's release
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) {
+          tc::tma_store_wait<0>();
+          fence_proxy_async_all();
+          __threadfence();
+          atomicAdd(ws_rec + pending_blk * kBlockRecInts, 1);
+#if MOE_TRACE
+          if (st_it - 1 < 13) TRACE(8 + 4 * (st_it - 1) + 3);
+#endif
+        }
+      }
+      __syncwarp();
+    }
+    if (lane == 0) {
+      int use[2] = {0, 0};
+      {   // staging-buffer uses of phase 1 (same count as above)
+        Item tt;
+        for (int it = 0; item1(g, it, p, P, rm, tt); ++it) ++use[it & 1];
+      }
+      uint32_t r_posted = 0;
+      Item t;
       const int consumers = g.n_tiles3 * g.split3;      // phase-3 items per row block
       for (int it = 0; item3(g, it, p, P, rm, t); ++it) {
         // wait until every phase-1 tile of the block is published, then route this item's share of the block:
         // consumer r of the block's `consumers` items takes chunks r, r + consumers, ...
         {
           const int* flag = ws_rec + t.m_blk * kBlockRecInts;
-          while (ld_acquire(flag) < g.n_tiles1) __nanosleep(40);
+          while (ld_acquire(flag) < g.n_tiles1) __nanosleep(32);
         }
         // the epilogue warps route this item's chunks (same formula there); count them for the block's consumers
         tc::mbar_arrive(&bars->route_req);
@@ -829,6 +910,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           __threadfence();
           atomicAdd(ws_rec + t.m_blk * kBlockRecInts + 1, mine);
         }
+        block_consumed(ws_rec + t.m_blk * kBlockRecInts, 2 * consumers);
         if (g.split3 == 1) {
           tc::mbar_wait(&bars->hs_full[0], use[0] & 1u);
           {   // clipped at T rows / d columns
@@ -845,7 +927,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           ++use[0];
         }
       }
-      tc::tma_store_wait<0>();
+      tc::tma_store_wait_read<0>();   // shared memory must outlive the reads; the writes complete with the kernel
     }
     __syncwarp();
   } else {
@@ -872,6 +954,9 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       for (int it = 0; item1(g, it, p, P, rm, t); ++it, ++acc_it) {
         const int as = acc_it & 1;
         const int buf = it & 1;
+#if MOE_TRACE
+        if (ew == 0 && lane == 0 && it >= 2 && it < 6) TRACE(40 + 4 * (it - 2));
+#endif
         float nb[4] = {0.f, 0.f, 0.f, 0.f};
         Item tn;
         const bool has_next = item1(g, it + 1, p, P, rm, tn);
@@ -887,7 +972,13 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             nb[3] = __ldg(bg + lane + 32);
           }
         }
+#if MOE_TRACE
+        if (ew == 0 && lane == 0 && it >= 2 && it < 6) TRACE(41 + 4 * (it - 2));
+#endif
         if (use[buf] > 0) tc::mbar_wait(&bars->hs_empty[buf], (use[buf] - 1) & 1u);   // staging buffer drained
+#if MOE_TRACE
+        if (ew == 0 && lane == 0 && it >= 2 && it < 6) TRACE(42 + 4 * (it - 2));
+#endif
         tc::mbar_wait(&bars->tmem_full[as], (acc_it >> 1) & 1u);
         tc::fence_after_thread_sync();
 #if MOE_TRACE
@@ -896,14 +987,19 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + as * kAccStride;
         const uint32_t hbase = tc::smem_u32(hstage + buf * g.hs_bytes);
         float* spart_row = spart + (buf * kBlockM + q_row) * kSpartPerRow;
+        const int row = t.m_blk * kBlockM + q_row;
+        float* score_dst = row < g.T ? a.scores + static_cast<size_t>(row) * g.E + t.n * g.experts_per_tile : nullptr;
         if (g.act == MOE_ACT_GELU)
-          geglu_group<CH, MOE_ACT_GELU>(g, taddr, sbias, hbase, hl1, q_row, spart_row, col0, cpg, cg);
+          geglu_group<CH, MOE_ACT_GELU>(g, taddr, sbias, hbase, hl1, q_row, spart_row, score_dst, col0, cpg, cg);
 #if MOE_TRACE
         else if (g.act == 2)
-          geglu_group<CH, 2>(g, taddr, sbias, hbase, hl1, q_row, spart_row, col0, cpg, cg);
+          geglu_group<CH, 2>(g, taddr, sbias, hbase, hl1, q_row, spart_row, score_dst, col0, cpg, cg);
 #endif
         else
-          geglu_group<CH, MOE_ACT_RELU>(g, taddr, sbias, hbase, hl1, q_row, spart_row, col0, cpg, cg);
+          geglu_group<CH, MOE_ACT_RELU>(g, taddr, sbias, hbase, hl1, q_row, spart_row, score_dst, col0, cpg, cg);
+#if MOE_TRACE
+        if (ew == 0 && lane == 0 && it >= 2 && it < 6) TRACE(43 + 4 * (it - 2));
+#endif
         // accumulator stage drained -> the leader's MMA thread may overwrite it
         tc::fence_before_thread_sync();
         __syncwarp();
@@ -913,23 +1009,6 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           sbias[lane + 32] = nb[1];
           sbias[64 + lane] = nb[2];
           sbias[64 + lane + 32] = nb[3];
-        }
-        // expert scores of this row: the 4 column-group warps of the lane quarter meet, the first one writes
-        tc::named_bar_sync(2 + q, 4 * 32);
-        if (cg == 0) {
-          const int row = t.m_blk * kBlockM + q_row;
-          if (row < g.T) {
-            float* dst = a.scores + static_cast<size_t>(row) * g.E + t.n * g.experts_per_tile;
-            if (g.experts_per_tile == 4 && g.span == 1 && (g.E & 3) == 0) {
-              *reinterpret_cast<float4*>(dst) = *reinterpret_cast<const float4*>(spart_row);
-            } else {
-              for (int e = 0; e < g.experts_per_tile; ++e) {
-                float tot = 0.f;
-                for (int j = 0; j < g.span; ++j) tot += spart_row[e * g.span + j];
-                dst[e] = tot;
-              }
-            }
-          }
         }
         // H tile: generic-proxy smem writes -> async proxy; the sync warp stores it and publishes the tile
         tc::fence_proxy_async_smem();
@@ -1078,21 +1157,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     for (int i = threadIdx.x; i < g.E; i += kNumThreads)
       if (s_hist[i]) atomicAdd(a.hist + i, static_cast<unsigned long long>(s_hist[i]));
   }
-  if (threadIdx.x == 0) {
-    __threadfence();
-    const int prev = atomicAdd(a.sync, 1);
-    bars->last_cta = (prev == static_cast<int>(gridDim.x) - 1);
-  }
   tc::cluster_sync_all();   // nobody exits while the peer may still signal its smem (also a CTA barrier)
   tc::fence_after_thread_sync();
-  if (bars->last_cta) {
-    // every other CTA is past its last access: leave the sync area clean for the next launch
-    for (int i = threadIdx.x; i < n_blocks; i += kNumThreads) {
-      ws_rec[i * kBlockRecInts] = 0;
-      ws_rec[i * kBlockRecInts + 1] = 0;
-    }
-    if (threadIdx.x == 0) a.sync[0] = 0;
-  }
   if (warp == 2) tc::tmem_dealloc_2sm<kTmemCols>(tmem_base);
   if (threadIdx.x == 0) TRACE(6);
 }
@@ -1314,7 +1380,18 @@ int moe_ffn_fused(const void* x, const void* w1p, const float* b1p, const void* 
     g.lanes = L;
     g.lanes_log2 = ilog2(L);
     g.kpt = kpt;
-    g.chunk_tokens = kEpiThreads / L;
+    // chunk size: a block's 128 tokens divided among (up to 32 of) its consumers, at least one warp's worth
+    int share = 1;
+    while (share * 2 <= consumers && share < 32) share <<= 1;
+    const int tpw = 32 / L;
+    int warps = (kBlockM / share) / tpw;
+    warps = warps < 1 ? 1 : (warps > kEpiWarps ? kEpiWarps : warps);
+    if (const char* e = getenv("MOE_FUSED_ROUTE_WARPS")) {
+      const int v = atoi(e);
+      if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) warps = v;
+    }
+    g.route_warps = warps;
+    g.chunk_tokens = tpw * warps;
     g.chunks_per_block = kBlockM / g.chunk_tokens;
     g.words = (E + 31) / 32;
   }
@@ -1327,9 +1404,9 @@ int moe_ffn_fused(const void* x, const void* w1p, const float* b1p, const void* 
   if (getenv("MOE_DEBUG_PRINT"))
     fprintf(stderr,
             "[moe_ffn_fused] T=%d d=%d h=%d E=%d es=%d k=%d | nv=%d tiles1=%d ks1=%d | bn=%d tiles3=%d split=%d ks3=%d kb/slice=%d | "
-            "stages=%d slot=%d | route lanes=%d kpt=%d chunks/block=%d | items %d + %d on %d pairs\n",
+            "stages=%d slot=%d | route lanes=%d kpt=%d warps=%d chunks/block=%d | items %d + %d on %d pairs\n",
             T, d, h, E, es, k, g.nv, g.n_tiles1, g.ks1, g.bn, g.n_tiles3, g.split3, g.ks3, g.kb_per_slice3, g.stages,
-            g.slot_bytes, g.lanes, g.kpt, g.chunks_per_block, g.items1, g.items3, P);
+            g.slot_bytes, g.lanes, g.kpt, g.route_warps, g.chunks_per_block, g.items1, g.items3, P);
 
   CUtensorMap tx, tw1, ths, thl, tw2, ty, ths_rem, ty_rem;
   int rc;

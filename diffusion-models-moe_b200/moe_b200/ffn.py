@@ -4,7 +4,8 @@
 up-projection weight, f32 biases, the (optionally packed) down-projection weight and the expert
 layout.  `moe_ffn_forward` is the whole hot path for one layer call:
 
-    K1 geglu_up  ->  K2 router_topk (select + histogram + zero inactive experts in H)  ->  K3 down_proj
+    moe_ffn_fused (one persistent kernel: up-projection -> routing -> down-projection), or, for geometries
+    it does not cover,  K1 geglu_up -> K2 router_topk (select + histogram + zero inactive experts) -> K3 down_proj
 """
 from dataclasses import dataclass
 from typing import Optional
@@ -12,7 +13,7 @@ from typing import Optional
 import torch
 import torch.nn as nn
 
-from . import ops
+from . import ops, _lib
 from .packing import ExpertLayout, pack_ffn
 from .sd_modules import GEGLU
 
@@ -28,6 +29,7 @@ class FFNState:
     act: int = ops.ACT_GELU
     weights_permuted_in_model: bool = False
     down_module: Optional[nn.Module] = None
+    fused_unsupported: bool = False      # set once moe_ffn_fused has rejected this geometry
 
     @property
     def n_experts(self) -> int:
@@ -143,6 +145,19 @@ def moe_ffn_forward(state: FFNState, x: torch.Tensor, *, removed_bits=None, hist
     lead = x.shape[:-1]
     xt = as_tokens(x)
     do_route = route and state.k is not None
+    w2 = state.w2p if w2_override is None else w2_override
+    if do_route and neuron_override is None and colmax_out is None and not state.fused_unsupported:
+        # one persistent kernel for the whole layer call (K1 -> routing -> K3); geometries it does not cover
+        # (MOE_ERR_UNSUPPORTED_SHAPE) use the three separate launches below -- both are the CUDA path
+        try:
+            y, _, _, bits, idx = ops.ffn_fused(xt, state.w1p, state.b1p, w2, state.b2, state.n_experts,
+                                               state.expert_size, state.k, state.act, removed_bits=removed_bits,
+                                               want_bits=want_bits, want_idx=want_idx, hist=hist, count_rows=count_rows)
+            return y.view(*lead, y.shape[-1]), bits, idx
+        except _lib.MoeLibraryError as e:
+            if "code -2" not in str(e):
+                raise
+            state.fused_unsupported = True
     H, scores, _ = ops.geglu_up(xt, state.w1p, state.b1p, state.n_experts, state.expert_size, state.act,
                                 neuron_override=neuron_override, override_value=override_value,
                                 want_scores=do_route)
@@ -151,5 +166,5 @@ def moe_ffn_forward(state: FFNState, x: torch.Tensor, *, removed_bits=None, hist
         bits, idx = ops.router_topk(scores, state.k, removed_bits=removed_bits, want_bits=want_bits, want_idx=want_idx,
                                     hist=hist, colmax_out=colmax_out, H=H, expert_size=state.expert_size,
                                     count_rows=count_rows)
-    y = ops.down_proj(H, state.w2p if w2_override is None else w2_override, state.b2)
+    y = ops.down_proj(H, w2, state.b2)
     return y.view(*lead, y.shape[-1]), bits, idx
