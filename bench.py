@@ -4,15 +4,17 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--experts reference|literal]
 
 One *step* = one denoising step of the hot path: the 16 transformer-block FFNs of the SD-1.5 UNet
-(BASELINE.json configs[1]: batch 2 = CFG, 64x64 latents, bf16), each as K1 geglu_up -> K2 router
-(+ fused row-0 expert histogram + masking) -> K3 down_proj, through the C ABI of libmoe_b200.so, on
-synthetic hidden states and random-init weights of the SD-1.5 geometry.
+(BASELINE.json configs[1]: batch 2 = CFG, 64x64 latents, bf16), each as ONE moe_ffn_fused launch (up-projection
++ GELU gate -> per-token top-k routing + row-0 expert histogram + masking -> down-projection; --path split runs the
+K1 geglu_up -> K2 router -> K3 down_proj launches instead), through the C ABI of libmoe_b200.so, on synthetic hidden
+states and random-init weights of the SD-1.5 geometry.
 
   value     tokens/s = token-FFN evaluations per second, whole job (N GPUs x 2 x 26 944 per step);
             inputs resident in HBM, the step replayed as one CUDA graph; time = CUDA events, max over ranks.
   e2e       same metric with HOST buffers: per step the 16 layer inputs are copied from pinned host memory,
-            the FFNs run through the C-ABI triple, outputs + histogram are copied back (all inside the timing).
-  roofline  dominant kernel (K1 geglu_up): algorithmic FLOPs (4 d h per token) / per-launch CUDA-event time.
+            the FFNs run through the C ABI, outputs + histogram are copied back (all inside the timing); copy-in,
+            compute and copy-out run on three streams chained per layer.
+  roofline  dominant kernel (ffn_fused_kernel): algorithmic FLOPs (6 d h per token) / CUDA-event time of its launches.
   cpu_baseline  the oracle port of the reference's hook arithmetic (fp32 torch-CPU, all host threads), timed
             here on rank 0 at N=1 on a bounded sample (one layer per distinct shape x multiplicity).
   --impl reference  times that CPU arm alone for K steps (the reference is pure Python on ATen and cannot be
@@ -193,28 +195,22 @@ def gpu_arm(args):
 
     fused = args.path == "fused"
 
-    def ffn_step(record=None):
+    def layer_call(li):
+        """One hooked FFN layer call on the current stream: fused kernel, or the K1 -> K2 -> K3 triple."""
+        L = layers[li]
+        p = L["p"]
         if fused:
-            for li, L in enumerate(layers):
-                p = L["p"]
-                M.ffn_fused(L["x"], p.w1p, p.b1p, p.w2p, p.b2, L["E"], L["es"], L["k"], M.ACT_GELU,
-                            hist=hist[li, :L["E"]], count_rows=(0, L["s"]), H_out=L["H"], scores_out=L["scores"],
-                            out=L["y"])
+            M.ffn_fused(L["x"], p.w1p, p.b1p, p.w2p, p.b2, L["E"], L["es"], L["k"], M.ACT_GELU,
+                        hist=hist[li, :L["E"]], count_rows=(0, L["s"]), H_out=L["H"], scores_out=L["scores"], out=L["y"])
             return
-        for li, L in enumerate(layers):
-            p = L["p"]
-            if record is not None:
-                record(li, 0)
-            M.geglu_up(L["x"], p.w1p, p.b1p, L["E"], L["es"], M.ACT_GELU, out=L["H"], scores_out=L["scores"])
-            if record is not None:
-                record(li, 1)
-            M.router_topk(L["scores"], L["k"], want_bits=False, hist=hist[li, :L["E"]], H=L["H"], expert_size=L["es"],
-                          count_rows=(0, L["s"]))
-            if record is not None:
-                record(li, 2)
-            M.down_proj(L["H"], p.w2p, p.b2, out=L["y"])
-            if record is not None:
-                record(li, 3)
+        M.geglu_up(L["x"], p.w1p, p.b1p, L["E"], L["es"], M.ACT_GELU, out=L["H"], scores_out=L["scores"])
+        M.router_topk(L["scores"], L["k"], want_bits=False, hist=hist[li, :L["E"]], H=L["H"], expert_size=L["es"],
+                      count_rows=(0, L["s"]))
+        M.down_proj(L["H"], p.w2p, p.b2, out=L["y"])
+
+    def ffn_step():
+        for li in range(len(layers)):
+            layer_call(li)
 
     def barrier():
         if world > 1:
@@ -312,25 +308,61 @@ def gpu_arm(args):
     h2d = sum(L["x_host"].numel() * 2 for L in layers)
     d2h = sum(L["y_host"].numel() * 2 for L in layers) + hist_host.numel() * 8
 
-    def e2e_step():
-        for L in layers:
-            L["x"].copy_(L["x_host"], non_blocking=True)
-        ffn_step()
-        for L in layers:
-            L["y_host"].copy_(L["y"], non_blocking=True)
-        hist_host.copy_(hist, non_blocking=True)
+    # Three streams, one per direction, chained per layer with events: the copy-in of layer l+1 and the copy-out of
+    # layer l-1 run on the two DMA engines while layer l computes; steps are serialised.
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    nL = len(layers)
+
+    def e2e_step(main):
+        """One step with host buffers on three streams forked from / joined into `main`."""
+        ev_in = [torch.cuda.Event() for _ in range(nL)]
+        ev_cmp = [torch.cuda.Event() for _ in range(nL)]
+        s_in.wait_stream(main)
+        s_out.wait_stream(main)
+        for li, L in enumerate(layers):
+            with torch.cuda.stream(s_in):
+                L["x"].copy_(L["x_host"], non_blocking=True)
+                ev_in[li].record(s_in)
+            main.wait_event(ev_in[li])
+            layer_call(li)
+            ev_cmp[li].record(main)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_cmp[li])
+                L["y_host"].copy_(L["y"], non_blocking=True)
+        with torch.cuda.stream(s_out):
+            hist_host.copy_(hist, non_blocking=True)
+        main.wait_stream(s_in)
+        main.wait_stream(s_out)       # the step's results (outputs + histogram) are on the host
 
     for _ in range(3):
-        e2e_step()
+        e2e_step(torch.cuda.current_stream())
+    torch.cuda.synchronize()
+    e2e_graph = None
+    if not args.no_graph:
+        # the same step as one CUDA graph (copies included), so that the 16 x (2 copies + launch) per step are not
+        # paced by the Python / ctypes host path
+        e2e_graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(e2e_graph, stream=side):
+                e2e_step(side)
+        torch.cuda.current_stream().wait_stream(side)
+        for _ in range(3):
+            e2e_graph.replay()
     barrier()
     n_e2e = min(args.steps, 20)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(n_e2e):
-        e2e_step()
+        if e2e_graph is not None:
+            e2e_graph.replay()
+        else:
+            e2e_step(torch.cuda.current_stream())
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1) / n_e2e
+    y_check = float(layers[0]["y_host"].float().abs().sum())      # the copied-back result is real data
 
     clocks = sampler.stop() if rank == 0 else None   # sampled across the timed region, the breakdown and e2e
     stats = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
@@ -356,14 +388,17 @@ def gpu_arm(args):
         # the step IS the dominant kernel: 16 launches of ffn_fused_kernel, nothing else in the timed region
         tf = (k1_flops + k3_flops) / (ms_step * 1e-3) / 1e12
         roofline = dict(bound="tensor", kernel="ffn_fused_kernel (K1 + routing + K3 per layer)", achieved=round(tf, 2),
-                        peak=peak_tf, unit="TFLOP/s", frac=round(tf / peak_tf, 4), traffic=None, peak_source=peak_src,
+                        peak=peak_tf, unit="TFLOP/s", frac=round(tf / peak_tf, 4),
+                        # ncu --set full, dram__bytes_read + write of one launch (profiles/r01_ncu_full_fused_layer_d320.csv;
+                        # d = 320, 8192 tokens: x 5.2 MB + weights 2.5 MB in, Y still in L2; H never leaves L2)
+                        traffic=8.18e6, traffic_launch="ffn_fused_kernel d=320 T=8192", peak_source=peak_src,
                         algorithmic="6*d*h FLOP per token (4dh up-projection + 2dh dense-equivalent down-projection), "
                                     "summed over the step's 16 launches / the step time (CUDA events; the timed region "
                                     "holds nothing but these launches)")
     else:
-      k1_tf = k1_flops / (per_kernel[0] * 1e-3) / 1e12
-      k3_tf = k3_flops / (per_kernel[2] * 1e-3) / 1e12
-      roofline = dict(bound="tensor", kernel="geglu_up_kernel (K1)", achieved=round(k1_tf, 2), peak=peak_tf,
+        k1_tf = k1_flops / (per_kernel[0] * 1e-3) / 1e12
+        k3_tf = k3_flops / (per_kernel[2] * 1e-3) / 1e12
+        roofline = dict(bound="tensor", kernel="geglu_up_kernel (K1)", achieved=round(k1_tf, 2), peak=peak_tf,
                     unit="TFLOP/s", frac=round(k1_tf / peak_tf, 4),
                     # ncu --set full, dram__bytes_read + write of the config-1 K1 launch (d=320, 8192 tokens; its
                     # algorithmic bytes are 30 MB, of which the 21 MB H tile stays in L2): profiles/r01_ncu_full_v6_*
@@ -387,7 +422,8 @@ def gpu_arm(args):
                             counters="row-0 expert histogram fused in the routing stage"),
                 unet_steps_per_s=world * 1e3 / ms_step,
                 e2e=dict(value=world * tokens_per_step / (ms_e2e * 1e-3), unit="tokens/s", h2d_bytes_per_step=h2d,
-                         d2h_bytes_per_step=d2h, ms_per_step=ms_e2e),
+                         d2h_bytes_per_step=d2h, ms_per_step=ms_e2e, cuda_graph=e2e_graph is not None,
+                         output_abs_sum_layer0=y_check),
                 gpu_launches=launches_per_step * args.steps, clocks=clocks, roofline=roofline,
                 histogram_counts_exact=counts_ok)
     if world == 1 and not args.no_cpu_baseline:
