@@ -473,17 +473,17 @@ __device__ __forceinline__ void route_chunk(const Shape& g, const Ptrs& a, int t
       if (tok >= tok_end) break;
       const uint32_t* wtok = s_words + tt * g.words;
       uint4* hrow = reinterpret_cast<uint4*>(a.H + static_cast<size_t>(tok) * g.h);
+      // two predicated 8-byte stores per 16-byte unit and no branches: a three-way if / else (16-byte store, or
+      // either half) made the warp run each store flavour in turn
+#pragma unroll 4
       for (int u = lane; u < units; u += 32) {
         const uint32_t ea = __umulhi(static_cast<uint32_t>(u) << 3, g.es_magic);
         const uint32_t eb = __umulhi((static_cast<uint32_t>(u) << 3) + 4u, g.es_magic);
         const bool on_a = (wtok[ea >> 5] >> (ea & 31u)) & 1u;
         const bool on_b = (wtok[eb >> 5] >> (eb & 31u)) & 1u;
-        if (!on_a && !on_b)
-          hrow[u] = make_uint4(0u, 0u, 0u, 0u);
-        else if (!on_a)
-          reinterpret_cast<uint2*>(hrow + u)[0] = make_uint2(0u, 0u);
-        else if (!on_b)
-          reinterpret_cast<uint2*>(hrow + u)[1] = make_uint2(0u, 0u);
+        uint2* half = reinterpret_cast<uint2*>(hrow + u);
+        if (!on_a) half[0] = make_uint2(0u, 0u);
+        if (!on_b) half[1] = make_uint2(0u, 0u);
       }
     }
   }
