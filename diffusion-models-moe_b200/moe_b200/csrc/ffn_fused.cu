@@ -1157,7 +1157,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     for (int i = threadIdx.x; i < g.E; i += kNumThreads)
       if (s_hist[i]) atomicAdd(a.hist + i, static_cast<unsigned long long>(s_hist[i]));
   }
-  tc::cluster_sync_all();   // nobody exits while the peer may still signal its smem (also a CTA barrier)
+  tc::cluster_sync_relaxed();   // nobody exits while the peer may still signal its smem (also a CTA barrier)
   tc::fence_after_thread_sync();
   if (warp == 2) tc::tmem_dealloc_2sm<kTmemCols>(tmem_base);
   if (threadIdx.x == 0) TRACE(6);
