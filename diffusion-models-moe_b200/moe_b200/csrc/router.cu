@@ -21,6 +21,7 @@ __device__ __forceinline__ uint32_t float_key(float s) {
 
 struct RouterArgs {
   const float* scores;
+  const float* score_bias;   // [E] added to the scores before the selection, or null (AddExperts)
   const uint32_t* removed_bits;
   uint32_t* active_bits;
   int16_t* idx;
@@ -47,11 +48,13 @@ __global__ void __launch_bounds__(kRouterWarps * 32) router_topk_kernel(const Ro
   __shared__ float s_max[kRouterWarps][SLOTS * 32];
 
   uint32_t removed[SLOTS], valid[SLOTS];
+  float bias[SLOTS];
 #pragma unroll
   for (int j = 0; j < SLOTS; ++j) {
     const int lo = 32 * j;
     valid[j] = (E >= lo + 32) ? full : (E > lo ? ((1u << (E - lo)) - 1u) : 0u);
     removed[j] = (a.removed_bits != nullptr && lo < E) ? (__ldg(a.removed_bits + j) & valid[j]) : 0u;
+    bias[j] = (a.score_bias != nullptr && lo + lane < E) ? __ldg(a.score_bias + lo + lane) : 0.f;
   }
 
   pdl_wait();                 // scores / H come from the previous kernel in the stream
@@ -74,6 +77,7 @@ __global__ void __launch_bounds__(kRouterWarps * 32) router_topk_kernel(const Ro
       if (e < E) {
         s = __ldg(row + e);
         mx[j] = fmaxf(mx[j], s);
+        s += bias[j];
       }
       if ((removed[j] >> lane) & 1u) s = 0.f;  // zeroed pattern row => score exactly 0
       key[j] = float_key(s);
@@ -301,6 +305,13 @@ extern "C" {
 int moe_router_topk(const float* scores, const uint32_t* removed_bits, int k, uint32_t* active_bits,
                     int16_t* idx, unsigned long long* hist, float* score_colmax, void* H, int h, int es,
                     int T, int E, int count_begin, int count_end, void* stream) {
+  return moe_router_topk_biased(scores, nullptr, removed_bits, k, active_bits, idx, hist, score_colmax, H, h, es, T, E,
+                                count_begin, count_end, stream);
+}
+
+int moe_router_topk_biased(const float* scores, const float* score_bias, const uint32_t* removed_bits, int k,
+                           uint32_t* active_bits, int16_t* idx, unsigned long long* hist, float* score_colmax, void* H,
+                           int h, int es, int T, int E, int count_begin, int count_end, void* stream) {
   using namespace moe;
   MOE_REQUIRE(scores != nullptr, MOE_ERR_INVALID_ARGUMENT, "moe_router_topk: scores is NULL");
   MOE_REQUIRE(T >= 0 && E >= 1 && k >= 0 && k <= E, MOE_ERR_INVALID_ARGUMENT,
@@ -315,6 +326,7 @@ int moe_router_topk(const float* scores, const uint32_t* removed_bits, int k, ui
   if (T == 0) return MOE_OK;
   RouterArgs a;
   a.scores = scores;
+  a.score_bias = score_bias;
   a.removed_bits = removed_bits;
   a.active_bits = active_bits;
   a.idx = idx;

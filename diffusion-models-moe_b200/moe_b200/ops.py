@@ -67,7 +67,7 @@ def geglu_up(x, w1p, b1p, n_experts: int, expert_size: int, act: int = ACT_GELU,
 
 
 def router_topk(scores, k: int, *, removed_bits=None, want_bits: bool = True, want_idx: bool = False, hist=None,
-                colmax_out=None, H=None, expert_size: int = 0, count_rows=(0, 0), bits_out=None):
+                colmax_out=None, H=None, expert_size: int = 0, count_rows=(0, 0), bits_out=None, score_bias=None):
     """K2.  scores f32 [T, E].  Returns (active_bits i32 [T, W] | None, idx i16 [T, k] | None).
     `hist` (int64 [E]) and `colmax_out` (f32 [E], pre-filled with -inf) are accumulated in place;
     `H` (bf16 [T, E*expert_size]) is zeroed in place for inactive experts."""
@@ -91,10 +91,12 @@ def router_topk(scores, k: int, *, removed_bits=None, want_bits: bool = True, wa
     if H is not None:
         h = E * expert_size
         _need(H, torch.bfloat16, "H", (T, h))
+    if score_bias is not None:
+        _need(score_bias, torch.float32, "score_bias", (E,))
     with torch.cuda.device(dev):
-        rc = lib.moe_router_topk(_ptr(scores), _ptr(removed_bits), int(k), _ptr(bits), _ptr(idx), _ptr(hist),
-                                 _ptr(colmax_out), _ptr(H), h, int(expert_size), T, E, int(count_rows[0]),
-                                 int(count_rows[1]), _stream(scores))
+        rc = lib.moe_router_topk_biased(_ptr(scores), _ptr(score_bias), _ptr(removed_bits), int(k), _ptr(bits), _ptr(idx),
+                                        _ptr(hist), _ptr(colmax_out), _ptr(H), h, int(expert_size), T, E,
+                                        int(count_rows[0]), int(count_rows[1]), _stream(scores))
     _lib.check(rc, "moe_router_topk")
     return bits, idx
 
@@ -218,6 +220,39 @@ def colmax(m, out=None):
     with torch.cuda.device(m.device):
         rc = fn(_ptr(m), T, C, _ptr(out), _stream(m))
     _lib.check(rc, "moe_colmax")
+    return out
+
+
+def colsum(m, out=None, row_mask=None):
+    """Column sums over rows of a [T, C] f32 matrix, accumulated into out (f32 [C], zero-filled if not given);
+    `row_mask` uint8 [period] keeps only rows t with row_mask[t % period] != 0."""
+    lib = _lib.load()
+    _need(m, torch.float32, "m")
+    T, C = m.shape
+    if out is None:
+        out = torch.zeros(C, dtype=torch.float32, device=m.device)
+    _need(out, torch.float32, "out", (C,))
+    period = 0
+    if row_mask is not None:
+        _need(row_mask, torch.uint8, "row_mask")
+        period = row_mask.numel()
+    with torch.cuda.device(m.device):
+        rc = lib.moe_colsum_f32(_ptr(m), T, C, _ptr(row_mask), period, _ptr(out), _stream(m))
+    _lib.check(rc, "moe_colsum_f32")
+    return out
+
+
+def rownorm_colsumsq(H, out=None):
+    """Squared column norms of the row-normalised bf16 matrix H [T, h], accumulated into out (f32 [h])."""
+    lib = _lib.load()
+    _need(H, torch.bfloat16, "H")
+    T, h = H.shape
+    if out is None:
+        out = torch.zeros(h, dtype=torch.float32, device=H.device)
+    _need(out, torch.float32, "out", (h,))
+    with torch.cuda.device(H.device):
+        rc = lib.moe_rownorm_colsumsq_bf16(_ptr(H), T, h, _ptr(out), _stream(H))
+    _lib.check(rc, "moe_rownorm_colsumsq_bf16")
     return out
 
 

@@ -96,6 +96,12 @@ MOE_API int moe_router_topk(const float* scores, const uint32_t* removed_bits, i
                     int16_t* idx, unsigned long long* hist, float* score_colmax, void* H, int h, int es,
                     int T, int E, int count_begin, int count_end, void* stream);
 
+/* Same with a per-expert bias added to the scores before the selection (score_bias f32 [E] or NULL; the column max
+ * is taken on the unbiased scores).  Replaces add_skilled_experts.py:53-58 (score[:, idx] += 5 * std[idx]; top-k). */
+MOE_API int moe_router_topk_biased(const float* scores, const float* score_bias, const uint32_t* removed_bits, int k,
+                    uint32_t* active_bits, int16_t* idx, unsigned long long* hist, float* score_colmax, void* H,
+                    int h, int es, int T, int E, int count_begin, int count_end, void* stream);
+
 /*
  * K3 -- down-projection Y = H W2p^T + b2 (tcgen05 / TMEM / TMA).  H has already been zeroed
  * for inactive experts by K2, so this is the dense-masked form; W2p may be the
@@ -138,6 +144,16 @@ MOE_API int moe_colmax_bf16(const void* m, int T, int C, float* out, void* strea
 MOE_API int moe_mask_pack(const uint8_t* dense, long long n, uint32_t* bits, void* stream);
 MOE_API int moe_mask_union(const uint32_t* a, const uint32_t* b, uint32_t* out, long long n_words, void* stream);
 MOE_API int moe_mask_weights(const void* w2, const uint32_t* bits, void* w2m, int d, int h, void* stream);
+
+/* Column sums out[c] += sum_t m[t, c] over the rows with row_mask[t % period] != 0 (row_mask u8 [period] or NULL =
+ * all rows).  Replaces get_experts.py:64-77 (score, optionally restricted to the bounding-box tokens of every batch
+ * row, averaged over tokens before the top-k).  out f32 [C], accumulated (caller zero-fills). */
+MOE_API int moe_colsum_f32(const float* m, int T, int C, const uint8_t* row_mask, int period, float* out, void* stream);
+/* out[n] += sum_t (H[t, n] / max(||H[t, :]||_2, 1e-12))^2 -- the squared column norms of the row-normalised hidden
+ * state.  Replaces wanda_receiver.py:47-53 + utils.py:330-337 (F.normalize(out, p=2, dim=1) then the incremental
+ * column norm sqrt(old^2 + new^2)): keep the squares on the device, take the root when the norms are read.
+ * H bf16 [T, h] (h % 8 == 0); out f32 [h], accumulated. */
+MOE_API int moe_rownorm_colsumsq_bf16(const void* H, int T, int h, float* out, void* stream);
 
 /*
  * Fused layer call -- the whole MoEfied GEGLU FFN of one BasicTransformerBlock in ONE persistent kernel:

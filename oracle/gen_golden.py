@@ -275,6 +275,78 @@ def case_wanda_csv_fixture(name):
          density=np.array([m.mean() for m in masks]), union_density=np.float64(union.mean()))
 
 
+@torch.no_grad()
+def case_get_experts(name, d, h, B, S, es, ratio, seed):
+    """GetExperts (get_experts.py): top-k of the token-averaged expert score, with and without a bounding box."""
+    layer = O.synthetic_layer(d, h, (B, S), es, seed)
+    mod = make_module(layer, ratio, O.ACT_GELU)
+    E = mod.patterns.shape[0]
+    rec = quiet(ref_nr.GetExperts, seed, 1, 16, {"l": E}, ["l"] * 16)
+    out = {}
+    bb = sorted(np.random.RandomState(seed).choice(S, S // 3, replace=False).tolist())
+    for tag, box in (("all", None), ("bb", bb)):
+        mod.bounding_box = box
+        rec.reset_time_layer()
+        H = rec.hook_fn(mod, (layer["x"],), None)
+        Ho, labels, mean = O.get_experts_labels(layer["x"], layer["w1"], layer["b1"], mod.patterns, mod.k, box)
+        assert torch.equal(H, Ho) and labels == rec.label_counter[0][0]
+        out[f"labels_{tag}"] = np.array(labels)
+        out[f"mean_{tag}"] = mean.numpy()
+    save(name, d=d, h=h, B=B, S=S, es=es, ratio=ratio, seed=seed, x=layer["x"].numpy(), w1=layer["w1"].numpy(),
+         b1=layer["b1"].numpy(), labels=layer["labels"], bb=np.array(bb), H=H.numpy(), **out)
+
+
+@torch.no_grad()
+def case_add_experts(name, d, h, B, S, es, ratio, seed):
+    """AddExperts (add_skilled_experts.py): boosted scores for the listed experts, top-int(0.8 k)."""
+    layer = O.synthetic_layer(d, h, (B, S), es, seed)
+    mod = make_module(layer, ratio, O.ACT_GELU)
+    E = mod.patterns.shape[0]
+    rs = np.random.RandomState(seed)
+    experts = sorted(rs.choice(E, 2, replace=False).tolist())
+    std = rs.uniform(0.5, 2.0, E).tolist()
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "adj", "skilled", "experts")
+        os.makedirs(path)
+        json.dump({"time_steps": {"0": {"0": {"std": std}}}}, open(os.path.join(td, "adj", "predictivity_base_expert.json"), "w"))
+        json.dump(experts, open(os.path.join(path, "timestep_0_layer_0.json"), "w"))
+        rec = quiet(ref_nr.AddExperts, seed, path, 1, 1)
+    H = rec.hook_fn(mod, (layer["x"],), None)
+    Ho, labels, gate, score = O.add_experts_forward(layer["x"], layer["w1"], layer["b1"], mod.patterns, mod.k, experts, std)
+    assert torch.equal(H, Ho) and torch.equal(rec.gates[0], gate)
+    kk = labels.shape[-1]
+    save(name, d=d, h=h, B=B, S=S, es=es, ratio=ratio, seed=seed, x=layer["x"].numpy(), w1=layer["w1"].numpy(),
+         b1=layer["b1"].numpy(), labels=layer["labels"], experts=np.array(experts), std=np.array(std), H=H.numpy(),
+         bitmask=O.labels_to_bitmask(labels.reshape(-1, kk), E), score=score.numpy(), margin=O.topk_margin(score, kk).numpy())
+
+
+@torch.no_grad()
+def case_wanda_receiver(name, d, h, B, S, es, seed, n_prompts=2):
+    """Wanda (wanda_receiver.py): incremental column norms of the row-normalised GEGLU output; SparsityMeasure
+    (sparsity_measure.py): captured activated gate, unmasked output."""
+    layer = O.synthetic_layer(d, h, (B, S), es, seed)
+    mod = make_module(layer, 1.0, O.ACT_RELU)
+    rec = quiet(ref_nr.Wanda, seed, 1, 1)
+    ssq = torch.zeros(h)
+    xs = []
+    for p in range(n_prompts):
+        x = torch.nn.functional.layer_norm(torch.randn(B, S, d, generator=torch.Generator().manual_seed(3000 + p)), (d,))
+        xs.append(x.numpy())
+        rec.reset_time_layer()
+        H = rec.hook_fn(mod, (x,), None)
+        v, g = O.geglu_up(x, layer["w1"], layer["b1"], O.ACT_RELU)
+        assert torch.equal(H, v * g)
+        ssq += O.wanda_column_sumsq(H)
+    norms = rec.predictivity.get_column_norms()[0][0]
+    assert torch.allclose(norms, torch.sqrt(ssq), rtol=1e-5, atol=1e-7)
+    sp = quiet(ref_nr.SparsityMeasure, seed)
+    Hs = sp.hook_fn(mod, (torch.from_numpy(xs[0]),), None)
+    v, g = O.geglu_up(torch.from_numpy(xs[0]), layer["w1"], layer["b1"], O.ACT_RELU)
+    assert torch.equal(Hs, v * g) and torch.equal(sp.gates[0], g)
+    save(name, d=d, h=h, B=B, S=S, es=es, seed=seed, xs=np.stack(xs), w1=layer["w1"].numpy(), b1=layer["b1"].numpy(),
+         labels=layer["labels"], column_norms=norms.numpy(), gate0=g.numpy(), H0=Hs.numpy())
+
+
 def main():
     torch.set_num_threads(max(1, (os.cpu_count() or 2) // 2))
     # small, fully stored cases (inputs + full outputs)
@@ -294,6 +366,10 @@ def main():
     case_remove_neurons("remove_neurons_small", 32, 128, 2, 48, 16, 0)
     case_wanda("wanda_small", 32, 128, 2, 24, 0)
     case_wanda_csv_fixture("wanda_csv_320_1280")
+    # the remaining receivers on the same primitives
+    case_get_experts("get_experts_small", 32, 128, 2, 48, 16, 0.3, 0)
+    case_add_experts("add_experts_small", 32, 128, 2, 48, 16, 0.6, 1)
+    case_wanda_receiver("wanda_receiver_small", 32, 128, 2, 24, 16, 2)
 
 
 if __name__ == "__main__":

@@ -193,6 +193,44 @@ def neuron_predictivity(gate_act: torch.Tensor) -> np.ndarray:
     return torch.max(gate_act.reshape(-1, gate_act.shape[-1]), dim=0)[0].detach().cpu().numpy()
 
 
+def get_experts_labels(x, w1, b1, patterns, k, bounding_box=None, act=ACT_GELU):
+    """GetExperts.hook_fn (get_experts.py:50-83): top-k (torch.topk order: descending score) of the expert score
+    AVERAGED over tokens -- all B*S tokens, or the bounding-box positions of every batch row -- and the unmasked
+    GEGLU output.  Returns (H, labels list[int], mean score [E])."""
+    v, g = geglu_up(x, w1, b1, act)
+    gate = g if g.dim() == 3 else g.unsqueeze(0)
+    h = gate.shape[-1]
+    if bounding_box is not None:
+        gate = gate[:, bounding_box, :]
+    mean = torch.matmul(gate.reshape(-1, h), patterns.transpose(0, 1)).mean(0)
+    labels = torch.topk(mean, k=k, dim=-1)[1]
+    return v * g, labels.reshape(-1).tolist(), mean
+
+
+def add_experts_forward(x, w1, b1, patterns, k, expert_idx: Sequence[int], std: Sequence[float], act=ACT_GELU):
+    """AddExperts.hook_fn (add_skilled_experts.py:37-62): the scores of the listed experts are raised by
+    5 * std[e] before a top-int(0.8 k) selection; masking as in MOEFy.  Returns (H, labels, gate_masked, score)."""
+    v, g = geglu_up(x, w1, b1, act)
+    lead, h = g.shape[:-1], g.shape[-1]
+    score = torch.matmul(g.reshape(-1, h), patterns.transpose(0, 1))
+    idx = list(expert_idx)
+    score[:, idx] = score[:, idx] + 5.0 * torch.tensor(std).to(g.dtype)[idx]
+    kk = int(0.8 * k)
+    labels = torch.topk(score, k=kk, dim=-1)[1].view(*lead, kk)
+    mask = torch.nn.functional.embedding(labels, patterns).sum(-2)
+    g = g.clone()
+    g[mask == 0] = 0
+    return v * g, labels, g, score
+
+
+def wanda_column_sumsq(h_out: torch.Tensor) -> torch.Tensor:
+    """Wanda.hook_fn (wanda_receiver.py:47-53) + ColumnNormCalculator.add_rows (utils.py:330-337): rows of the
+    GEGLU output are L2-normalised, the column norms accumulate as sqrt(old^2 + new^2); this returns the squared
+    column norms of ONE call (the quantity that adds up)."""
+    rows = torch.nn.functional.normalize(h_out.reshape(-1, h_out.shape[-1]), p=2, dim=1)
+    return torch.norm(rows, dim=0) ** 2
+
+
 class TimeLayerClock:
     """(timestep, layer) state machine advanced once per hook call
     (predictivity.py:25-30; frequency_measure.py:24-29 hard-codes n_layers-1 == 15)."""

@@ -238,3 +238,85 @@ def test_observe_activation_on_sd15_ffn_stack(lib):
     m = nr.MOEFy(0, capture_gates=False)
     out2, _ = m.observe_activation(pipe, "a photo of a cat")
     assert all(torch.isfinite(t.float()).all() for t in out2)
+
+
+# ------------------------------------------------------------------ remaining receivers
+def test_get_experts_hook(lib, golden_dir):
+    """GetExperts (get_experts.py:50-83): top-k of the token-averaged score, all tokens and bounding-box tokens."""
+    g = load(golden_dir, "get_experts_small")
+    ff = make_ff(g, float(g["ratio"]), with_down=False)
+    mod = ff.net[0]
+    E = mod.patterns.shape[0]
+    rec = nr.GetExperts(0, 1, 16, {"l": E}, ["l"] * 16)
+    x = T(g["x"]).to(DEV, torch.bfloat16)
+    for tag, box in (("all", None), ("bb", g["bb"].tolist())):
+        mod.bounding_box = box
+        rec.reset_time_layer()
+        H = rec.hook_fn(mod, (x,), None)
+        mean = rec.mean_score[0][0]
+        want_mean = g[f"mean_{tag}"]
+        assert np.allclose(mean, want_mean, atol=0.05)                    # bf16 inputs vs the fp32 reference
+        # exact mean of the kernel's own scores (oracle on bf16-rounded inputs), labels = top-k of that vector
+        pat = O.patterns_from_labels(g["labels"])
+        _, labels, m16 = O.get_experts_labels(r16(T(g["x"])), r16(T(g["w1"])), T(g["b1"]), pat, mod.k, box)
+        assert np.allclose(mean, m16.numpy(), atol=1e-3)                  # per-token scores agree to 5e-4 (gpu_util.SCORE_ATOL)
+        srt = np.sort(m16.numpy())[::-1]
+        if srt[mod.k - 1] - srt[mod.k] > 5e-3:                            # clear margin: identical label SET
+            assert set(rec.label_counter[0][0]) == set(labels)
+        assert rec.label_counter[0][0] == torch.topk(torch.from_numpy(mean), mod.k)[1].tolist()
+    assert rel_err(unpack_cols(H, mod), T(g["H"])) < OUT_REL_TOL          # unmasked output
+    mod.bounding_box = None
+
+
+def test_add_experts_hook(lib, golden_dir, tmp_path):
+    """AddExperts (add_skilled_experts.py:37-62): boosted experts are always selected, k' = int(0.8 k)."""
+    g = load(golden_dir, "add_experts_small")
+    experts, std = g["experts"].tolist(), g["std"].tolist()
+    path = tmp_path / "adj" / "skilled" / "experts"
+    os.makedirs(path)
+    json.dump({"time_steps": {"0": {"0": {"std": std}}}}, open(tmp_path / "adj" / "predictivity_base_expert.json", "w"))
+    json.dump(experts, open(path / "timestep_0_layer_0.json", "w"))
+    ff = make_ff(g, float(g["ratio"]), with_down=False)
+    mod = ff.net[0]
+    rec = nr.AddExperts(0, str(path), 1, 1)
+    H = rec.hook_fn(mod, (T(g["x"]).to(DEV, torch.bfloat16),), None)
+    pat = O.patterns_from_labels(g["labels"])
+    Ho, labels, gate, score = O.add_experts_forward(r16(T(g["x"])), r16(T(g["w1"])), T(g["b1"]), pat, mod.k, experts, std)
+    kk = labels.shape[-1]
+    safe = (O.topk_margin(score, kk) > 2e-3).numpy()
+    Hc = unpack_cols(H, mod).reshape(-1, H.shape[-1])
+    Hor = Ho.reshape(-1, H.shape[-1])
+    assert safe.mean() > 0.85 and rel_err(Hc[safe], Hor[safe]) < OUT_REL_TOL
+    # every token keeps the boosted experts' neurons (their score was raised by >= 2.5)
+    live = torch.stack([(Hc[:, np.nonzero(pat[e].numpy())[0]] != 0).any(1) for e in range(pat.shape[0])], 1)
+    for e in experts:
+        assert bool(live[:, e].all())
+    assert int(live.sum(1).max()) <= kk
+    assert rec.gates and rel_err(unpack_cols(rec.gates[0].to(DEV), mod).reshape(-1, H.shape[-1])[safe],
+                                 gate.reshape(-1, H.shape[-1])[safe]) < OUT_REL_TOL
+
+
+def test_wanda_receiver_and_sparsity_measure(lib, golden_dir):
+    """Wanda (wanda_receiver.py:37-57): column norms of the row-normalised output accumulated over two prompts;
+    SparsityMeasure (sparsity_measure.py:13-18): captured activated gate, unmasked output."""
+    g = load(golden_dir, "wanda_receiver_small")
+    ff = make_ff(g, 1.0, with_down=False)
+    mod = ff.net[0]
+    mod.gelu = torch.nn.functional.relu
+    rec = nr.Wanda(0, 1, 1)
+    for x in g["xs"]:
+        rec.reset_time_layer()
+        H = rec.hook_fn(mod, (T(x).to(DEV, torch.bfloat16),), None)
+    norms = rec.predictivity.get_column_norms()[0][0].numpy()
+    norms = norms if mod._moe_state.weights_permuted_in_model is False else norms[mod._moe_state.layout.inv_perm.numpy()]
+    assert np.allclose(norms, g["column_norms"], rtol=2e-2, atol=2e-3)     # bf16 H vs fp32 reference
+    # exact restatement on the kernel's own (bf16) H of the last call
+    last = O.wanda_column_sumsq(H.float().cpu())
+    one = nr.Wanda(0, 1, 1)
+    one.hook_fn(mod, (T(g["xs"][-1]).to(DEV, torch.bfloat16),), None)
+    assert torch.allclose(one.predictivity.sumsq[(0, 0)].cpu(), last, rtol=1e-4, atol=1e-6)
+    sp = nr.SparsityMeasure(0)
+    Hs = sp.hook_fn(mod, (T(g["xs"][0]).to(DEV, torch.bfloat16),), None)
+    assert rel_err(unpack_cols(Hs, mod), T(g["H0"])) < OUT_REL_TOL
+    assert rel_err(unpack_cols(sp.gates[0].to(DEV), mod), T(g["gate0"])) < OUT_REL_TOL
+    assert bool(torch.all(sp.gates[0] >= 0)) and 0.3 < sp.zero_fraction() < 0.7      # ReLU: about half exact zeros

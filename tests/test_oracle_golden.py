@@ -135,3 +135,37 @@ def test_topk_ratio_table():
     assert [O.topk_from_ratio(64, r / 10) for r in range(1, 11)] == [6, 12, 19, 25, 32, 38, 44, 51, 57, 64]
     assert [O.topk_from_ratio(256, r / 10) for r in range(1, 11)] == [25, 51, 76, 102, 128, 153, 179, 204, 230, 256]
     assert [O.topk_from_ratio(20, r / 10) for r in range(1, 11)] == [2, 4, 6, 8, 10, 12, 14, 16, 18, 20]
+
+
+# ------------------------------------------------------------------ remaining receivers
+def test_get_experts(golden_dir):
+    g = load(golden_dir, "get_experts_small")
+    pat = O.patterns_from_labels(g["labels"])
+    k = O.topk_from_ratio(pat.shape[0], float(g["ratio"]))
+    for tag, box in (("all", None), ("bb", g["bb"].tolist())):
+        H, labels, mean = O.get_experts_labels(T(g["x"]), T(g["w1"]), T(g["b1"]), pat, k, box)
+        assert labels == g[f"labels_{tag}"].tolist()
+        assert np.array_equal(mean.numpy(), g[f"mean_{tag}"])
+    assert torch.equal(H, T(g["H"]))
+
+
+def test_add_experts(golden_dir):
+    g = load(golden_dir, "add_experts_small")
+    pat = O.patterns_from_labels(g["labels"])
+    k = O.topk_from_ratio(pat.shape[0], float(g["ratio"]))
+    H, labels, gate, score = O.add_experts_forward(T(g["x"]), T(g["w1"]), T(g["b1"]), pat, k, g["experts"].tolist(),
+                                                   g["std"].tolist())
+    assert torch.equal(H, T(g["H"])) and np.array_equal(score.numpy(), g["score"])
+    assert np.array_equal(O.labels_to_bitmask(labels.reshape(-1, labels.shape[-1]), pat.shape[0]), g["bitmask"])
+    assert labels.shape[-1] == int(0.8 * k)
+
+
+def test_wanda_receiver_column_norms(golden_dir):
+    g = load(golden_dir, "wanda_receiver_small")
+    ssq = torch.zeros(int(g["h"]))
+    for x in g["xs"]:
+        v, gate = O.geglu_up(T(x), T(g["w1"]), T(g["b1"]), O.ACT_RELU)
+        ssq += O.wanda_column_sumsq(v * gate)
+    assert np.allclose(torch.sqrt(ssq).numpy(), g["column_norms"], rtol=1e-5, atol=1e-7)
+    v, gate = O.geglu_up(T(g["xs"][0]), T(g["w1"]), T(g["b1"]), O.ACT_RELU)
+    assert torch.equal(gate, T(g["gate0"])) and torch.equal(v * gate, T(g["H0"]))     # SparsityMeasure
