@@ -464,7 +464,7 @@ __device__ __forceinline__ void route_chunk(const Shape& g, const Ptrs& a, int t
   if (ew == 0 && lane == 0) TRACE(58);
 #endif
 
-  if (g.mask_h && g.k < E) {
+  if (g.mask_h && (g.k < E || a.removed_bits != nullptr)) {   // k == E still masks the removed experts' neurons
     // materialise the masked hidden state: zero the neurons of every expert outside the token's active set
     // (write-only; 16-byte units, 4-neuron groups never straddle an expert because es % 4 == 0)
     const int units = g.h >> 3;

@@ -83,6 +83,22 @@ def test_fused_removed_experts_and_count_window(lib):
     assert same[O.topk_margin(un["scores"], un["k"]).numpy() > 1e-3].all()
 
 
+def test_fused_removed_experts_with_k_equal_E(lib):
+    """ratio 1.0 (moefy_config.yaml:5) with a removal list: every expert is selected, the removed ones still own no
+    neurons (remove_skilled_experts.py:29-35 zeroes their pattern rows) -- found by tools/stress_fused.py."""
+    layer = O.synthetic_layer(128, 640, (2, 150), 20, seed=9)
+    removed = [3, 4, 17, 31]
+    cu = fused_layer(layer, 1.0, removed=removed)
+    un = cuda_layer(layer, 1.0, removed=removed)
+    orc = oracle_layer(layer, 1.0, removed=removed, timestep=0)
+    n = 300
+    dead = orc["pat"][removed].sum(0) > 0
+    assert torch.all(cu["H"].reshape(n, -1)[:, dead] == 0)
+    assert torch.equal(cu["H"], un["H"]) and rel_err(cu["y"], un["y"]) < 2e-3
+    assert rel_err(cu["H"], orc["H"]) < OUT_REL_TOL and rel_err(cu["y"], orc["y"]) < OUT_REL_TOL
+    assert all(s == set(range(32)) - set(removed) for s in cu["sets"])
+
+
 def test_fused_repeat_launches_share_workspace(lib):
     """The sync counters are left at zero by every launch: back-to-back launches on one workspace, of different
     geometries, give the same results as fresh ones."""
@@ -117,6 +133,18 @@ def test_fused_without_masking_is_the_dense_ffn(lib):
         assert rel_err(b["H"], dense["H_unmasked"]) < 1e-6
         assert rel_err(b["y"], dense["y"]) < 2e-3
         assert (a["H"] == 0).float().mean() > 0.6                 # ~70 % of the neurons masked at ratio 0.3
+
+
+def test_fused_randomised_against_separate_kernels(lib):
+    """tools/stress_fused.py: 80 random (geometry, token count, ratio, activation, removal list, count window) cases;
+    every case runs the fused kernel three times on the shared workspace (bit-identical repeats) and must agree
+    with the K1 -> K2 -> K3 path: identical labels / histograms, routing bit-exact on its own scores, same Y."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "tools", "stress_fused.py"), "80", "3"], capture_output=True,
+                         text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
+    assert "80 cases, 0 failures" in res.stdout
 
 
 def test_fused_unsupported_geometry_raises(lib):
