@@ -27,6 +27,8 @@ SIGNATURES = {
                                        c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "moe_colsum_f32": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "moe_rownorm_colsumsq_bf16": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "moe_wanda_score_mask": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "moe_mask_vote": (c_int, [c_void_p, c_int, c_ll, c_float, c_void_p, c_void_p]),
     "moe_down_proj": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, ctypes.c_size_t,
                               c_void_p]),
     "moe_down_proj_workspace_bytes": (ctypes.c_size_t, [c_int, c_int, c_int]),

@@ -135,6 +135,23 @@ __device__ __forceinline__ int ld_acquire(const int* p) {
   return v;
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// Poll a cross-CTA counter until it reaches `target`.  A protocol bug or a workspace that was not zero (e.g. left
+// dirty by an aborted launch) would otherwise hang the GPU until an external timeout; the watchdog turns a wait of
+// more than 2 s into a trap (launch failure reported to the host), like tc::mbar_wait does for mbarriers.
+__device__ __forceinline__ void poll_at_least(const int* flag, int target) {
+  uint32_t spins = 0;
+  uint64_t t0 = 0;
+  while (ld_acquire(flag) < target) {
+    __nanosleep(32);
+    if ((++spins & 0xFFFu) == 0) {
+      const uint64_t now = tc::global_timer_ns();
+      if (t0 == 0)
+        t0 = now;
+      else if (now - t0 > 2000000000ull)
+        __trap();
+    }
+  }
+}
 
 __device__ __forceinline__ uint64_t pk2(float lo, float hi) {
   uint64_t r;
@@ -713,8 +730,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 #if MOE_TRACE
             if (it == 0) TRACE(62);
 #endif
-            const int* flag = ws_rec + t.m_blk * kBlockRecInts + 1;
-            while (ld_acquire(flag) < g.chunks_per_block) __nanosleep(32);
+            poll_at_least(ws_rec + t.m_blk * kBlockRecInts + 1, g.chunks_per_block);
 #if MOE_TRACE
             if (it == 0) TRACE(63);
 #endif
@@ -896,10 +912,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       for (int it = 0; item3(g, it, p, P, rm, t); ++it) {
         // wait until every phase-1 tile of the block is published, then route this item's share of the block:
         // consumer r of the block's `consumers` items takes chunks r, r + consumers, ...
-        {
-          const int* flag = ws_rec + t.m_blk * kBlockRecInts;
-          while (ld_acquire(flag) < g.n_tiles1) __nanosleep(32);
-        }
+        poll_at_least(ws_rec + t.m_blk * kBlockRecInts, g.n_tiles1);
         // the epilogue warps route this item's chunks (same formula there); count them for the block's consumers
         tc::mbar_arrive(&bars->route_req);
         tc::mbar_wait(&bars->route_done, r_posted & 1u);

@@ -256,6 +256,36 @@ def rownorm_colsumsq(H, out=None):
     return out
 
 
+def wanda_score_mask(w2, norm_base, norm_adj, k: int, out=None):
+    """Wanda mask bits of one (timestep, layer): w2 bf16 [d, h], norms f32 [h] -> int32 [d*h/32]."""
+    lib = _lib.load()
+    d, h = w2.shape
+    _need(w2, torch.bfloat16, "w2")
+    _need(norm_base, torch.float32, "norm_base", (h,))
+    _need(norm_adj, torch.float32, "norm_adj", (h,))
+    if out is None:
+        out = torch.empty(d * h // 32, dtype=torch.int32, device=w2.device)
+    _need(out, torch.int32, "out", (d * h // 32,))
+    with torch.cuda.device(w2.device):
+        rc = lib.moe_wanda_score_mask(_ptr(w2), _ptr(norm_base), _ptr(norm_adj), d, h, int(k), _ptr(out), _stream(w2))
+    _lib.check(rc, "moe_wanda_score_mask")
+    return out
+
+
+def mask_vote(masks, threshold: float, out=None):
+    """masks int32 [T, n_words] -> int32 [n_words]: bit set where more than `threshold` of the T masks have it."""
+    lib = _lib.load()
+    _need(masks, torch.int32, "masks")
+    Tn, n = masks.shape
+    if out is None:
+        out = torch.empty(n, dtype=torch.int32, device=masks.device)
+    _need(out, torch.int32, "out", (n,))
+    with torch.cuda.device(masks.device):
+        rc = lib.moe_mask_vote(_ptr(masks), Tn, n, float(threshold), _ptr(out), _stream(masks))
+    _lib.check(rc, "moe_mask_vote")
+    return out
+
+
 def mask_pack(dense):
     """dense uint8 0/1 (any shape, n elements) -> int32 [ceil(n/32)] bit words (bit i%32 of word i/32)."""
     lib = _lib.load()

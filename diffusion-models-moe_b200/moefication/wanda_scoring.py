@@ -1,0 +1,48 @@
+"""Wanda scoring and union-over-timesteps baking on the device.
+
+    score_masks(w2, norms_base, norms_adj, ratio)      reference modularity/wanda.py:140-173
+    union_over_time(mask_bits, select_ratio)           reference benchmarks/save_union_over_time.py:189-211
+    bake(linear, union_bits)                           reference benchmarks/save_union_over_time.py:219-227
+
+Masks are bit words over the row-major [d, h] weight (the layout `moe_mask_weights` consumes); `to_csr` converts one
+back to the scipy CSR matrix the reference pickles (`timestep_{t}_layer_{l}.pkl`)."""
+import numpy as np
+import torch
+
+from moe_b200 import ops
+
+
+def score_masks(w2: torch.Tensor, norms_base, norms_adj, ratio: float) -> torch.Tensor:
+    """w2 [d, h] (any float dtype, on the GPU); norms_* = sequence over timesteps of f32 [h] column norms
+    (Wanda receiver `get_column_norms()[t][l]`).  Returns int32 [T, d*h/32] mask bits."""
+    d, h = w2.shape
+    k = int(ratio * h)
+    w = w2.detach().to(torch.bfloat16).contiguous()
+    out = torch.empty(len(norms_adj), d * h // 32, dtype=torch.int32, device=w.device)
+    for t, (nb, na) in enumerate(zip(norms_base, norms_adj)):
+        ops.wanda_score_mask(w, nb.to(w.device, torch.float32).contiguous(), na.to(w.device, torch.float32).contiguous(), k,
+                             out=out[t])
+    return out
+
+
+def union_over_time(mask_bits: torch.Tensor, select_ratio: float) -> torch.Tensor:
+    """mask_bits int32 [T, n_words] -> int32 [n_words]: kept where set at more than select_ratio * T timesteps."""
+    return ops.mask_vote(mask_bits.contiguous(), select_ratio * mask_bits.shape[0])
+
+
+@torch.no_grad()
+def bake(linear: torch.nn.Module, union_bits: torch.Tensor) -> None:
+    """ff.net.2 weight *= (1 - mask), in place (the baked "union-timesteps" checkpoint of the reference)."""
+    w = linear.weight
+    masked = ops.mask_weights(w.detach().to(torch.bfloat16).contiguous(), union_bits)
+    w.data.copy_(masked.to(w.dtype))
+
+
+def to_dense(bits: torch.Tensor, d: int, h: int) -> np.ndarray:
+    words = bits.detach().cpu().numpy().view(np.uint32)
+    return np.unpackbits(words.view(np.uint8), bitorder="little")[: d * h].reshape(d, h).astype(int)
+
+
+def to_csr(bits: torch.Tensor, d: int, h: int):
+    import scipy.sparse
+    return scipy.sparse.csr_matrix(to_dense(bits, d, h))

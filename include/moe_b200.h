@@ -155,6 +155,16 @@ MOE_API int moe_colsum_f32(const float* m, int T, int C, const uint8_t* row_mask
  * H bf16 [T, h] (h % 8 == 0); out f32 [h], accumulated. */
 MOE_API int moe_rownorm_colsumsq_bf16(const void* H, int T, int h, float* out, void* stream);
 
+/* Wanda scoring of one (timestep, layer): bit (r*h + c) of `bits` := (|W2[r,c]| * norm_adj[c] > |W2[r,c]| * norm_base[c])
+ * AND c is among the k = int(ratio * h) largest |W2[r,:]| * norm_adj of row r (ties on the k-th value: lowest column).
+ * Replaces modularity/wanda.py:143-165 (two row-wise torch.sort over [d, h], scatter_, compare, CSR pickle).
+ * w2 bf16 [d, h]; norm_* f32 [h]; bits u32 [d*h/32] out (the layout moe_mask_weights / moe_mask_union use). */
+MOE_API int moe_wanda_score_mask(const void* w2, const float* norm_base, const float* norm_adj, int d, int h, int k,
+                    uint32_t* bits, void* stream);
+/* Union over timesteps by vote: out bit i := #{t : bit i of masks[t]} > threshold.  Replaces
+ * benchmarks/save_union_over_time.py:192-205 (sum of T CSR masks > select_ratio * T).  masks u32 [T][n_words]. */
+MOE_API int moe_mask_vote(const uint32_t* masks, int T, long long n_words, float threshold, uint32_t* out, void* stream);
+
 /*
  * Fused layer call -- the whole MoEfied GEGLU FFN of one BasicTransformerBlock in ONE persistent kernel:
  * up-projection + activation + product + expert scores (as moe_geglu_up), per-token top-k routing with the

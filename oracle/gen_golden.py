@@ -347,6 +347,46 @@ def case_wanda_receiver(name, d, h, B, S, es, seed, n_prompts=2):
          labels=layer["labels"], column_norms=norms.numpy(), gate0=g.numpy(), H0=Hs.numpy())
 
 
+def reference_lines(relpath, first, last):
+    """Source lines [first, last] (1-based) of a reference script, dedented: the scripts below are `main()`s with
+    file I/O around the arithmetic, so the arithmetic itself is executed from their own text."""
+    import textwrap
+    with open(os.path.join(REF, relpath)) as f:
+        lines = f.readlines()[first - 1:last]
+    return textwrap.dedent("".join(lines))
+
+
+@torch.no_grad()
+def case_wanda_scoring(name, d, h, ratio, seed, T=6, select_ratio=0.5):
+    """Wanda scoring (modularity/wanda.py:143-165) and union over timesteps (save_union_over_time.py:189-211), both
+    run from the reference's own source text on synthetic weights / norms."""
+    import scipy.sparse
+    rs = np.random.RandomState(seed)
+    w2 = torch.from_numpy(rs.standard_normal((d, h)).astype(np.float32)).to(torch.bfloat16).float()
+    masks, nb, na = [], [], []
+    for t in range(T):
+        norm_base = torch.from_numpy(np.abs(rs.standard_normal(h)).astype(np.float32))
+        norm_adj = norm_base * torch.from_numpy(rs.uniform(0.5, 1.5, h).astype(np.float32))
+        norm_adj[rs.choice(h, h // 16, replace=False)] = 0.0          # dead neurons (ReLU-fied model)
+        ns = dict(torch=torch, np=np, scipy=scipy, gate_weights={"l": w2.abs()}, layer_names=["l"], l=0, t=0,
+                  act_norms_base={0: {0: norm_base}}, act_norms_adj={0: {0: norm_adj}}, sparsity_ratio=ratio, print=lambda *a: None)
+        exec(reference_lines("modularity/wanda.py", 143, 165), ns)
+        ref_mask = ns["binary_mask"].numpy().astype(int)
+        assert np.array_equal(O.wanda_score_mask(w2.abs(), norm_base, norm_adj, ratio), ref_mask)
+        masks.append(ref_mask); nb.append(norm_base.numpy()); na.append(norm_adj.numpy())
+    with tempfile.TemporaryDirectory() as td:
+        for t, m in enumerate(masks):
+            with open(os.path.join(td, f"timestep_{t}_layer_0.pkl"), "wb") as f:
+                pickle.dump(scipy.sparse.csr_matrix(m), f)
+        ns = dict(np=np, scipy=scipy, pickle=pickle, os=os, path=td, n_layers=1, timesteps=T, weights_shape=[(d, h)],
+                  select_ratio=select_ratio, layer_names=["l"], print=lambda *a: None, masks={})
+        exec(reference_lines("benchmarks/save_union_over_time.py", 189, 211), ns)
+    union = np.asarray(ns["masks"]["l"]).astype(int)
+    assert np.array_equal(O.union_over_time(masks, select_ratio), union)
+    save(name, d=d, h=h, ratio=ratio, T=T, select_ratio=select_ratio, w2=w2.numpy(), norm_base=np.stack(nb), norm_adj=np.stack(na),
+         masks=np.packbits(np.stack(masks).astype(np.uint8), axis=-1), union=np.packbits(union.astype(np.uint8), axis=-1))
+
+
 def main():
     torch.set_num_threads(max(1, (os.cpu_count() or 2) // 2))
     # small, fully stored cases (inputs + full outputs)
@@ -370,6 +410,8 @@ def main():
     case_get_experts("get_experts_small", 32, 128, 2, 48, 16, 0.3, 0)
     case_add_experts("add_experts_small", 32, 128, 2, 48, 16, 0.6, 1)
     case_wanda_receiver("wanda_receiver_small", 32, 128, 2, 24, 16, 2)
+    # Wanda scoring and the union over timesteps
+    case_wanda_scoring("wanda_scoring_small", 64, 256, 0.05, 3)
 
 
 if __name__ == "__main__":

@@ -231,6 +231,28 @@ def wanda_column_sumsq(h_out: torch.Tensor) -> torch.Tensor:
     return torch.norm(rows, dim=0) ** 2
 
 
+def wanda_score_mask(w2_abs: torch.Tensor, norm_base: torch.Tensor, norm_adj: torch.Tensor, ratio: float) -> np.ndarray:
+    """modularity/wanda.py:143-165: metric = |W2| * column norm (base / adj prompts); a weight is a skilled-neuron
+    weight iff its adj metric exceeds its base metric AND it is among the int(ratio * h) largest adj metrics of its
+    output row.  Returns the dense {0,1} int mask [d, h]."""
+    metric_base = w2_abs * norm_base
+    metric_adj = w2_abs * norm_adj
+    k = int(ratio * metric_adj.shape[1])
+    _, order = torch.sort(metric_adj, dim=1, descending=True)
+    top = torch.zeros_like(w2_abs)
+    top.scatter_(1, order[:, :k], 1)
+    return ((metric_adj > metric_base) * top).numpy().astype(int)
+
+
+def union_over_time(masks: Sequence[np.ndarray], select_ratio: float) -> np.ndarray:
+    """benchmarks/save_union_over_time.py:192-209: a weight stays masked iff it is masked at more than
+    select_ratio * T of the T timesteps."""
+    total = np.zeros_like(np.asarray(masks[0]), dtype=np.int64)
+    for m in masks:
+        total += np.asarray(m)
+    return (total > (select_ratio * len(masks))).astype(int)
+
+
 class TimeLayerClock:
     """(timestep, layer) state machine advanced once per hook call
     (predictivity.py:25-30; frequency_measure.py:24-29 hard-codes n_layers-1 == 15)."""

@@ -320,3 +320,30 @@ def test_wanda_receiver_and_sparsity_measure(lib, golden_dir):
     assert rel_err(unpack_cols(Hs, mod), T(g["H0"])) < OUT_REL_TOL
     assert rel_err(unpack_cols(sp.gates[0].to(DEV), mod), T(g["gate0"])) < OUT_REL_TOL
     assert bool(torch.all(sp.gates[0] >= 0)) and 0.3 < sp.zero_fraction() < 0.7      # ReLU: about half exact zeros
+
+
+def test_wanda_scoring_and_union_kernels_bit_exact(lib, golden_dir):
+    """moe_wanda_score_mask / moe_mask_vote / bake against the fixture made from the reference's own source lines
+    (modularity/wanda.py:143-165, save_union_over_time.py:189-227): integer masks, bit-exact."""
+    from moefication import wanda_scoring as ws
+    g = load(golden_dir, "wanda_scoring_small")
+    d, h, Tn = int(g["d"]), int(g["h"]), int(g["T"])
+    w2 = T(g["w2"]).to(DEV)
+    bits = ws.score_masks(w2, [T(v) for v in g["norm_base"]], [T(v) for v in g["norm_adj"]], float(g["ratio"]))
+    want = np.unpackbits(g["masks"], axis=-1)[..., :h].astype(int)
+    for t in range(Tn):
+        assert np.array_equal(ws.to_dense(bits[t], d, h), want[t]), t
+    union = ws.union_over_time(bits, float(g["select_ratio"]))
+    want_u = np.unpackbits(g["union"], axis=-1)[..., :h].astype(int)
+    assert np.array_equal(ws.to_dense(union, d, h), want_u)
+    lin = torch.nn.Linear(h, d).to(DEV, torch.bfloat16)
+    with torch.no_grad():
+        lin.weight.copy_(w2)
+    ws.bake(lin, union)
+    assert torch.equal(lin.weight.float().cpu(), T(g["w2"]) * torch.from_numpy(1 - want_u).float())
+    assert ws.to_csr(union, d, h).nnz == int(want_u.sum())
+    # ties on the k-th value go to the lowest column: a row of equal metrics keeps exactly the first k columns
+    flat = torch.ones(2, 64, dtype=torch.bfloat16, device=DEV)
+    nb, na = torch.zeros(64, device=DEV), torch.ones(64, device=DEV)
+    tb = ws.to_dense(ws.score_masks(flat, [nb], [na], 0.25)[0], 2, 64)
+    assert tb[:, :16].all() and not tb[:, 16:].any()

@@ -169,3 +169,18 @@ def test_wanda_receiver_column_norms(golden_dir):
     assert np.allclose(torch.sqrt(ssq).numpy(), g["column_norms"], rtol=1e-5, atol=1e-7)
     v, gate = O.geglu_up(T(g["xs"][0]), T(g["w1"]), T(g["b1"]), O.ACT_RELU)
     assert torch.equal(gate, T(g["gate0"])) and torch.equal(v * gate, T(g["H0"]))     # SparsityMeasure
+
+
+def test_wanda_scoring_and_union_over_time(golden_dir):
+    """modularity/wanda.py:143-165 and save_union_over_time.py:189-211 (fixtures produced by executing those lines)."""
+    g = load(golden_dir, "wanda_scoring_small")
+    d, h, Tn = int(g["d"]), int(g["h"]), int(g["T"])
+    want = np.unpackbits(g["masks"], axis=-1)[..., :h].astype(int)
+    masks = []
+    for t in range(Tn):
+        m = O.wanda_score_mask(T(g["w2"]).abs(), T(g["norm_base"][t]), T(g["norm_adj"][t]), float(g["ratio"]))
+        assert np.array_equal(m, want[t])
+        assert m.sum(1).max() <= int(float(g["ratio"]) * h)
+        masks.append(m)
+    union = O.union_over_time(masks, float(g["select_ratio"]))
+    assert np.array_equal(union, np.unpackbits(g["union"], axis=-1)[..., :h].astype(int))
