@@ -98,6 +98,7 @@ struct Shape {
   int m_pairs;                                  // 256-row work units
   // phase 1
   int nv, n_tiles1, ks1, nkb1, items1;
+  int step_m1, step_n1;                         // a pair's next phase-1 tile: (mp, n) += (step_m1, step_n1), carry n -> mp
   int experts_per_tile, chunks_per_expert, span;
   // phase 3
   int bn, n_tiles3, ks3, nkb3, split3, kb_per_slice3, items3;
@@ -135,15 +136,30 @@ __device__ __forceinline__ int ld_acquire(const int* p) {
   return v;
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// generic-proxy accesses to global memory (here: writes of other SMs that this thread has just acquired) before this
+// thread's async-proxy (TMA) accesses to global memory: one FENCE.VIEW.ASYNC.G instead of the all-space form's
+// GPU-scope membar + L1 invalidate
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+__device__ __forceinline__ int atom_add_acq_rel(int* p, int v) {
+  int old;
+  asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+  return old;
+}
+// counter += v with release semantics at GPU scope: every write this thread has performed or observed (the tile's
+// scores through the hs_full barrier, the H tile through cp.async.bulk.wait_group) is visible to whoever acquires
+// the new count.  One MEMBAR.ALL.GPU + RED; the __threadfence() + fence.proxy.async pair used before cost two
+// GPU-scope membars and two L1 invalidations (1.6 us per tile, which made the store warp pace phase 1).
+__device__ __forceinline__ void red_release_add(int* p, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 // Poll a cross-CTA counter until it reaches `target`.  A protocol bug or a workspace that was not zero (e.g. left
 // dirty by an aborted launch) would otherwise hang the GPU until an external timeout; the watchdog turns a wait of
 // more than 2 s into a trap (launch failure reported to the host), like tc::mbar_wait does for mbarriers.
 __device__ __forceinline__ void poll_at_least(const int* flag, int target) {
   uint32_t spins = 0;
   uint64_t t0 = 0;
-  while (ld_acquire(flag) < target) {
-    __nanosleep(32);
-    if ((++spins & 0xFFFu) == 0) {
+  while (ld_acquire(flag) < target) {   // one lane per CTA polls its own block's 128-byte record: no back-off needed
+    if ((++spins & 0xFFFFu) == 0) {
       const uint64_t now = tc::global_timer_ns();
       if (t0 == 0)
         t0 = now;
@@ -587,9 +603,25 @@ __device__ __forceinline__ void stage_store(uint32_t base, const StageLayout& l,
   }
 }
 
+// the same with the pieces' byte offsets computed once per kernel (they depend on the thread's row and column group
+// only): `off[i]` = offset of 4-column piece i of the chunk; `aligned` = the chunk starts on an 8-column boundary
+template <int kWords>
+__device__ __forceinline__ void stage_store_pre(uint32_t base, const uint32_t* off, bool aligned, const uint32_t* w) {
+  if (aligned) {
+#pragma unroll
+    for (int i = 0; i + 4 <= kWords; i += 4) tc::sts_b32x4(base + off[i / 2], w[i], w[i + 1], w[i + 2], w[i + 3]);
+    if constexpr (kWords % 4 != 0) tc::sts_b32x2(base + off[kWords / 2 - 1], w[kWords - 2], w[kWords - 1]);
+  } else {
+    tc::sts_b32x2(base + off[0], w[0], w[1]);
+#pragma unroll
+    for (int i = 2; i + 4 <= kWords; i += 4) tc::sts_b32x4(base + off[i / 2], w[i], w[i + 1], w[i + 2], w[i + 3]);
+    if constexpr (kWords % 4 == 0) tc::sts_b32x2(base + off[kWords / 2 - 1], w[kWords - 2], w[kWords - 1]);
+  }
+}
+
 template <int CH, int ACT>
 __device__ __forceinline__ void geglu_group(const Shape& g, uint32_t taddr, const float* sbias, uint32_t hbase,
-                                            const StageLayout& hl, int q_row, float* spart_row, float* score_dst,
+                                            const uint32_t* piece_off, bool aligned, float* spart_row, float* score_dst,
                                             int col0, int cpg, int cg) {
   uint64_t score2 = pk2(0.f, 0.f);
   int chunk_in_expert = 0, e_slot = (g.chunks_per_expert > 0) ? cg * (cpg / g.es) : cg;
@@ -627,7 +659,7 @@ __device__ __forceinline__ void geglu_group(const Shape& g, uint32_t taddr, cons
       hw[i / 2] = pack_bf16x2(h0, h1);
       hw[i / 2 + 1] = pack_bf16x2(h2, h3);
     }
-    stage_store<CH / 2>(hbase, hl, q_row, col0 + c, hw);
+    stage_store_pre<CH / 2>(hbase, piece_off + c / 4, aligned, hw);
     if (g.chunks_per_expert > 0 && ++chunk_in_expert == g.chunks_per_expert) {
       float s0, s1;
       unpk2(score2, s0, s1);
@@ -667,7 +699,6 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   const int rm = static_cast<int>(tc::cluster_ctarank());
   const int p = static_cast<int>(blockIdx.x) >> 1, P = static_cast<int>(gridDim.x) >> 1;
   int* const ws_rec = a.sync + kSyncHeaderInts;                        // per block: [0] done, [1] ready
-  const int n_blocks = 2 * g.m_pairs;
 
   if (warp == 0 && lane == 0) {
     tc::prefetch_tensormap(&tmap_x);
@@ -737,7 +768,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             block_consumed(ws_rec + t.m_blk * kBlockRecInts, 2 * g.n_tiles3 * g.split3);
           }
           __syncwarp();
-          fence_proxy_async_all();   // generic-proxy writes of other SMs (acquired above) -> this thread's TMA reads
+          fence_proxy_async_global();   // generic-proxy writes of other SMs (acquired above) -> this thread's TMA reads
         }
         for (int kb = t.kb_begin; kb < t.kb_end; kb += ks) {
           tc::mbar_wait(&bars->empty[s], ph ^ 1u);
@@ -842,6 +873,9 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       for (int it = 0; item1(g, it, p, P, rm, t); ++it, ++st_it) {
         const int buf = st_it & 1;
         tc::mbar_wait(&bars->hs_full[buf], use_p1[buf] & 1u);
+#if MOE_TRACE
+        if (lane == 0 && it >= 2 && it < 6) TRACE(40 + 4 * (it - 2));
+#endif
         if (lane == 0) {
           const uint8_t* src = hstage + buf * g.hs_bytes;
           const int n_full = g.nv >> 6;
@@ -870,13 +904,18 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         if (lane == 0) {
           tc::tma_store_wait_read<0>();
           tc::mbar_arrive(&bars->hs_empty[buf]);   // the epilogue warps may refill the buffer
+#if MOE_TRACE
+          if (it >= 2 && it < 6) TRACE(41 + 4 * (it - 2));
+#endif
           if (pending_blk >= 0) {
             tc::tma_store_wait<1>();        // every group but the one just committed is globally written
-            fence_proxy_async_all();
-            __threadfence();                // previous H tile + its scores before the count
-            atomicAdd(ws_rec + pending_blk * kBlockRecInts, 1);
+#if MOE_TRACE
+            if (it >= 2 && it < 6) TRACE(42 + 4 * (it - 2));
+#endif
+            red_release_add(ws_rec + pending_blk * kBlockRecInts, 1);   // previous H tile + its scores, then the count
 #if MOE_TRACE
             if (st_it - 1 < 13) TRACE(8 + 4 * (st_it - 1) + 3);
+            if (it >= 2 && it < 6) TRACE(43 + 4 * (it - 2));
 #endif
           }
         }
@@ -885,14 +924,10 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         __syncwarp();
       }
       if (pending_blk >= 0) {
-        // the last tile's scores were written by all lanes: order them before lane 0's release
-        __threadfence();
-        __syncwarp();
+        __syncwarp();   // (span mode: the lanes' score stores above are already fenced)
         if (lane == 0) {
           tc::tma_store_wait<0>();
-          fence_proxy_async_all();
-          __threadfence();
-          atomicAdd(ws_rec + pending_blk * kBlockRecInts, 1);
+          red_release_add(ws_rec + pending_blk * kBlockRecInts, 1);
 #if MOE_TRACE
           if (st_it - 1 < 13) TRACE(8 + 4 * (st_it - 1) + 3);
 #endif
@@ -919,10 +954,9 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         ++r_posted;
         int mine = 0;
         for (int c = t.n * g.split3 + t.slice; c < g.chunks_per_block; c += consumers) ++mine;
-        if (mine > 0) {
-          __threadfence();
-          atomicAdd(ws_rec + t.m_blk * kBlockRecInts + 1, mine);
-        }
+        // release at GPU scope: the epilogue threads' labels / zero-writes were ordered before route_done (mbarrier
+        // arrive = release.cta, wait = acquire.cta), the release is cumulative over them
+        if (mine > 0) red_release_add(ws_rec + t.m_blk * kBlockRecInts + 1, mine);
         block_consumed(ws_rec + t.m_blk * kBlockRecInts, 2 * consumers);
         if (g.split3 == 1) {
           tc::mbar_wait(&bars->hs_full[0], use[0] & 1u);
@@ -959,22 +993,36 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     {
       const int cpg = g.nv / 4;
       const int col0 = cg * cpg;
+      // per-thread constants of the loop: byte offsets of this thread's 4-column pieces inside a staging buffer
+      // (row q_row, columns col0 ...) and whether the column group starts on an 8-column boundary
+      uint32_t piece_off[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) piece_off[i] = (4 * i < cpg) ? stage_addr(0u, hl1, q_row, col0 + 4 * i) : 0u;
+      const bool aligned = ((col0 | CH) & 7) == 0 || (col0 & 7) == 0;
+      // tile coordinates advance by a fixed step per iteration: no divisions in the loop
+      int i1 = p, mp1 = p / g.n_tiles1, n1 = p - (p / g.n_tiles1) * g.n_tiles1;
       // bias slices: the first tile's are staged up front, every later tile's are fetched into registers while
       // the previous tile is being processed (a staged load per tile exposed ~0.8 us of global latency each time)
-      if (item1(g, 0, p, P, rm, t))
-        stage_bias(sbias, a.b1 != nullptr ? a.b1 + t.n * g.nv + col0 : nullptr,
-                   a.b1 != nullptr ? a.b1 + g.h + t.n * g.nv + col0 : nullptr, cpg, lane);
-      for (int it = 0; item1(g, it, p, P, rm, t); ++it, ++acc_it) {
+      if (i1 < g.items1)
+        stage_bias(sbias, a.b1 != nullptr ? a.b1 + n1 * g.nv + col0 : nullptr,
+                   a.b1 != nullptr ? a.b1 + g.h + n1 * g.nv + col0 : nullptr, cpg, lane);
+      for (int it = 0; i1 < g.items1; ++it, ++acc_it) {
+        t.m_blk = 2 * mp1 + rm;
+        t.n = n1;
+        // next tile of this pair
+        i1 += P;
+        mp1 += g.step_m1;
+        n1 += g.step_n1;
+        if (n1 >= g.n_tiles1) {
+          n1 -= g.n_tiles1;
+          ++mp1;
+        }
         const int as = acc_it & 1;
         const int buf = it & 1;
-#if MOE_TRACE
-        if (ew == 0 && lane == 0 && it >= 2 && it < 6) TRACE(40 + 4 * (it - 2));
-#endif
         float nb[4] = {0.f, 0.f, 0.f, 0.f};
-        Item tn;
-        const bool has_next = item1(g, it + 1, p, P, rm, tn);
+        const bool has_next = i1 < g.items1;
         if (has_next && a.b1 != nullptr) {
-          const float* bv = a.b1 + tn.n * g.nv + col0;
+          const float* bv = a.b1 + n1 * g.nv + col0;
           const float* bg = bv + g.h;
           if (lane < cpg) {
             nb[0] = __ldg(bv + lane);
@@ -985,13 +1033,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             nb[3] = __ldg(bg + lane + 32);
           }
         }
-#if MOE_TRACE
-        if (ew == 0 && lane == 0 && it >= 2 && it < 6) TRACE(41 + 4 * (it - 2));
-#endif
         if (use[buf] > 0) tc::mbar_wait(&bars->hs_empty[buf], (use[buf] - 1) & 1u);   // staging buffer drained
-#if MOE_TRACE
-        if (ew == 0 && lane == 0 && it >= 2 && it < 6) TRACE(42 + 4 * (it - 2));
-#endif
         tc::mbar_wait(&bars->tmem_full[as], (acc_it >> 1) & 1u);
         tc::fence_after_thread_sync();
 #if MOE_TRACE
@@ -1003,16 +1045,13 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         const int row = t.m_blk * kBlockM + q_row;
         float* score_dst = row < g.T ? a.scores + static_cast<size_t>(row) * g.E + t.n * g.experts_per_tile : nullptr;
         if (g.act == MOE_ACT_GELU)
-          geglu_group<CH, MOE_ACT_GELU>(g, taddr, sbias, hbase, hl1, q_row, spart_row, score_dst, col0, cpg, cg);
+          geglu_group<CH, MOE_ACT_GELU>(g, taddr, sbias, hbase, piece_off, aligned, spart_row, score_dst, col0, cpg, cg);
 #if MOE_TRACE
         else if (g.act == 2)
-          geglu_group<CH, 2>(g, taddr, sbias, hbase, hl1, q_row, spart_row, score_dst, col0, cpg, cg);
+          geglu_group<CH, 2>(g, taddr, sbias, hbase, piece_off, aligned, spart_row, score_dst, col0, cpg, cg);
 #endif
         else
-          geglu_group<CH, MOE_ACT_RELU>(g, taddr, sbias, hbase, hl1, q_row, spart_row, score_dst, col0, cpg, cg);
-#if MOE_TRACE
-        if (ew == 0 && lane == 0 && it >= 2 && it < 6) TRACE(43 + 4 * (it - 2));
-#endif
+          geglu_group<CH, MOE_ACT_RELU>(g, taddr, sbias, hbase, piece_off, aligned, spart_row, score_dst, col0, cpg, cg);
         // accumulator stage drained -> the leader's MMA thread may overwrite it
         tc::fence_before_thread_sync();
         __syncwarp();
@@ -1048,9 +1087,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         for (int c = t.n * g.split3 + t.slice; c < g.chunks_per_block; c += g.n_tiles3 * g.split3)
           route_dispatch(g, a, t.m_blk * kBlockM + c * g.chunk_tokens, min(g.T, (t.m_blk + 1) * kBlockM), ew, lane, s_words,
                          s_hist);
-        __threadfence();     // labels / expert sets visible device-wide before the sync warp counts the chunks
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&bars->route_done);
+        __syncwarp();        // every lane's zero-writes / labels before lane 0's arrive (release at CTA scope; the sync
+        if (lane == 0) tc::mbar_arrive(&bars->route_done);   // warp's red.release then publishes them device-wide)
 #if MOE_TRACE
         if (ew == 0 && lane == 0) TRACE(61);
 #endif
@@ -1112,18 +1150,18 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           tc::fence_before_thread_sync();
           __syncwarp();
           if (lane == 0) tc::mbar_arrive_cluster(tc::mapa_u32(&bars->tmem_empty[as], 0));
-          __threadfence();
+          // all partial stores of the CTA, then ONE acquire-release increment: it publishes this slice's partial tile
+          // and, for the last slice to arrive, acquires the other slices' (which are then read from L2 with ld.cg)
           tc::named_bar_sync(1, kEpiThreads);
           if (ew == 0 && lane == 0) {
             int* counter = a.split_counters + t.m_blk * g.n_tiles3 + t.n;
-            const int prev = atomicAdd(counter, 1);
+            const int prev = atom_add_acq_rel(counter, 1);
             const int last = prev == g.split3 - 1;
             if (last) *counter = 0;
             bars->last_cta = last;
           }
           tc::named_bar_sync(1, kEpiThreads);
           if (bars->last_cta) {
-            __threadfence();
             const int et = ew * 32 + lane;
             const int cols4 = g.bn >> 2;
             const int tile_col0 = t.n * g.bn;
@@ -1285,6 +1323,8 @@ int moe_ffn_fused(const void* x, const void* w1p, const float* b1p, const void* 
   g.n_tiles1 = h / nv;
   g.nkb1 = d / kBlockK;
   g.items1 = g.m_pairs * g.n_tiles1;
+  g.step_m1 = (sm_count() / 2) / g.n_tiles1;
+  g.step_n1 = (sm_count() / 2) % g.n_tiles1;
   g.experts_per_tile = nv / es;
   g.chunks_per_expert = (cpg1 % es == 0) ? es / ch1 : 0;
   g.span = (cpg1 % es == 0) ? 1 : es / cpg1;

@@ -37,8 +37,8 @@ def show(name, tr, ms):
         print(f"   item {it:2d}: mma-commit {col(b)} | epi-begin {col(b+1)} | epi-done {col(b+2)} | stored+signalled {col(b+3)}")
     print(f"   route: first begin {col(60)} | last end {col(61)} | K3 A-producer: ready-wait begin {col(62)} end {col(63)}")
     for i in range(4):
-        print(f"   K1 tile {i+2} (warp 4): loop top {col(40+4*i)} | bias prefetch issued {col(41+4*i)} | hs_empty passed {col(42+4*i)} | "
-              f"tmem_full passed {col(9+4*(i+2))} | math done {col(43+4*i)} | tile done {col(10+4*(i+2))}")
+        print(f"   sync warp, tile {i+2}: hs_full seen {col(40+4*i)} | stores read, buffer released {col(41+4*i)} | "
+              f"previous tile's stores complete {col(42+4*i)} | previous tile published {col(43+4*i)}")
     def d(i, j):
         c = rel[:, j] - rel[:, i]; c = c[~torch.isnan(c)]
         return f"{c.min():5.2f}/{c.median():5.2f}/{c.max():5.2f}" if len(c) else "-"
