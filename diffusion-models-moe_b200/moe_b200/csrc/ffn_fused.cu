@@ -140,9 +140,11 @@ __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.pr
 // thread's async-proxy (TMA) accesses to global memory: one FENCE.VIEW.ASYNC.G instead of the all-space form's
 // GPU-scope membar + L1 invalidate
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
-__device__ __forceinline__ int atom_add_acq_rel(int* p, int v) {
+// returns the old value; release at GPU scope (the partial tiles read afterwards come from L2 with ld.cg, so no L1
+// invalidation -- the acquire half of an acq_rel atomic -- is needed)
+__device__ __forceinline__ int atom_add_release(int* p, int v) {
   int old;
-  asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+  asm volatile("atom.release.gpu.global.add.s32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
   return old;
 }
 // counter += v with release semantics at GPU scope: every write this thread has performed or observed (the tile's
@@ -372,6 +374,36 @@ __device__ __forceinline__ void route_chunk(const Shape& g, const Ptrs& a, int t
   if (g.k >= E) {
     sel = valid;
   } else if (g.k > 0) {
+    uint32_t prefix;
+    if (L == 32) {
+      // a whole warp per token: MSB-first bisection on the keys, one full-mask REDUX per round (~60 cycles of
+      // dependent latency per round, ~20 rounds) -- a single warp walks the 36-stage sorting network of 256 keys in
+      // ~4000 cycles, three times as long
+      uint32_t k_or = 0u, k_and = full;
+#pragma unroll
+      for (int i = 0; i < KPT; ++i)
+        if ((valid >> i) & 1u) {
+          k_or |= key[i];
+          k_and &= key[i];
+        }
+      k_or = __reduce_or_sync(full, k_or);
+      k_and = __reduce_and_sync(full, k_and);
+      const uint32_t diff = k_or ^ k_and;
+      prefix = k_and;                       // every valid key identical
+      if (diff != 0u && t_ok) {
+        const int top = 31 - __clz(diff);
+        prefix = (top == 31) ? 0u : (k_and & ~((2u << top) - 1u));
+        for (int bit = top; bit >= 0; --bit) {
+          const uint32_t thr = prefix | (1u << bit);
+          int c = 0;
+#pragma unroll
+          for (int i = 0; i < KPT; ++i) c += (key[i] >= thr) ? 1 : 0;
+          c = __reduce_add_sync(full, c);
+          if (c >= g.k) prefix = thr;
+          if (c == g.k) break;              // exactly k keys at or above the threshold: done (warp-uniform)
+        }
+      }
+    } else {
     // k-th largest key of the token: bitonic sort of its N = KPT * L keys (element i = part * KPT + r; invalid
     // slots hold key 0 and sink to the bottom), compare-exchanges inside a lane for distances < KPT and through
     // shuffles beyond.  ~250 instructions and ~700 cycles per pass regardless of the data; the MSB-first bisection
@@ -425,7 +457,8 @@ __device__ __forceinline__ void route_chunk(const Shape& g, const Ptrs& a, int t
     uint32_t mine = 0u;
 #pragma unroll
     for (int r = 0; r < KPT; ++r) mine = (r == (pos & (KPT - 1))) ? srt[r] : mine;
-    const uint32_t prefix = __shfl_sync(full, mine, (lane & ~(L - 1)) + pos / KPT);
+    prefix = __shfl_sync(full, mine, (lane & ~(L - 1)) + pos / KPT);
+    }
     // keys above the k-th value, then ties on it from the lowest expert id
     uint32_t gt = 0u, eq = 0u;
 #pragma unroll
@@ -1150,12 +1183,12 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           tc::fence_before_thread_sync();
           __syncwarp();
           if (lane == 0) tc::mbar_arrive_cluster(tc::mapa_u32(&bars->tmem_empty[as], 0));
-          // all partial stores of the CTA, then ONE acquire-release increment: it publishes this slice's partial tile
-          // and, for the last slice to arrive, acquires the other slices' (which are then read from L2 with ld.cg)
+          // all partial stores of the CTA, then ONE releasing increment: it publishes this slice's partial tile; the
+          // last slice to arrive reads the other slices' tiles from L2 (ld.cg) after the barrier below
           tc::named_bar_sync(1, kEpiThreads);
           if (ew == 0 && lane == 0) {
             int* counter = a.split_counters + t.m_blk * g.n_tiles3 + t.n;
-            const int prev = atom_add_acq_rel(counter, 1);
+            const int prev = atom_add_release(counter, 1);
             const int last = prev == g.split3 - 1;
             if (last) *counter = 0;
             bars->last_cta = last;
