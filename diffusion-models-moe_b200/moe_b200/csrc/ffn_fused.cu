@@ -160,7 +160,12 @@ __device__ __forceinline__ void red_release_add(int* p, int v) {
 __device__ __forceinline__ void poll_at_least(const int* flag, int target) {
   uint32_t spins = 0;
   uint64_t t0 = 0;
-  while (ld_acquire(flag) < target) {   // one lane per CTA polls its own block's 128-byte record: no back-off needed
+  // one lane per CTA polls its own block's 128-byte record: relaxed loads (an acquire load is LDG + CCTL.IVALL, an
+  // L1 invalidation per iteration), one acquire load once the count is there
+  for (;;) {
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    if (v >= target) break;
     if ((++spins & 0xFFFFu) == 0) {
       const uint64_t now = tc::global_timer_ns();
       if (t0 == 0)
@@ -169,6 +174,7 @@ __device__ __forceinline__ void poll_at_least(const int* flag, int target) {
         __trap();
     }
   }
+  (void)ld_acquire(flag);   // the acquire (and its one L1 invalidation) once the count is there
 }
 
 __device__ __forceinline__ uint64_t pk2(float lo, float hi) {
@@ -901,7 +907,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       // column groups are combined here from shared-memory partial sums.
       int st_it = 0;
       int use_p1[2] = {0, 0};
-      int pending_blk = -1;
+      int pending_blk = -1, prev_blk = -1;
       Item t;
       for (int it = 0; item1(g, it, p, P, rm, t); ++it, ++st_it) {
         const int buf = st_it & 1;
@@ -940,7 +946,11 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 #if MOE_TRACE
           if (it >= 2 && it < 6) TRACE(41 + 4 * (it - 2));
 #endif
-          if (pending_blk >= 0) {
+          Item nx;
+          prev_blk = -1;
+          if (pending_blk >= 0 && !item1(g, it + 1, p, P, rm, nx)) {
+            prev_blk = pending_blk;         // last tile: its predecessor is published together with it, after the loop
+          } else if (pending_blk >= 0) {
             tc::tma_store_wait<1>();        // every group but the one just committed is globally written
 #if MOE_TRACE
             if (it >= 2 && it < 6) TRACE(42 + 4 * (it - 2));
@@ -959,8 +969,12 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       if (pending_blk >= 0) {
         __syncwarp();   // (span mode: the lanes' score stores above are already fenced)
         if (lane == 0) {
+          // the critical path of the phase: one wait for the outstanding stores, ONE release fence, then the counts
+          // of the last tile and (if it was deferred) of its predecessor
           tc::tma_store_wait<0>();
-          red_release_add(ws_rec + pending_blk * kBlockRecInts, 1);
+          asm volatile("fence.acq_rel.gpu;" ::: "memory");
+          if (prev_blk >= 0) atomicAdd(ws_rec + prev_blk * kBlockRecInts, 1);
+          atomicAdd(ws_rec + pending_blk * kBlockRecInts, 1);
 #if MOE_TRACE
           if (st_it - 1 < 13) TRACE(8 + 4 * (st_it - 1) + 3);
 #endif
