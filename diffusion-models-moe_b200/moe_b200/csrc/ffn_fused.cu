@@ -102,6 +102,7 @@ struct Shape {
   int experts_per_tile, chunks_per_expert, span;
   // phase 3
   int bn, n_tiles3, ks3, nkb3, split3, kb_per_slice3, items3;
+  long long split_plane4;                       // float4 elements between two K slices of the split-K partial tiles
   // pipeline
   int stages, slot_bytes, hs_bytes;             // hs_bytes: one phase-1 staging buffer (two of them; phase 3 uses both)
   // routing
@@ -1178,25 +1179,29 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           if (lane == 0) tc::mbar_arrive(&bars->hs_full[0]);
           ++use[0];
         } else {
-          // ---- split-K: park this slice's fp32 partial tile; the last slice to arrive reduces in slice order
-          const size_t plane = static_cast<size_t>(g.T) * g.d;
-          float* part = a.split_partial + t.slice * plane + static_cast<size_t>(row) * g.d + n0;
+          // ---- split-K: park this slice's fp32 partial tile; the last slice to arrive reduces in slice order.
+          // Partial tiles live in a tile-local layout [slice][tile][16-byte column chunk][row]: a thread owns a row, so a
+          // warp's 32 stores of one chunk are 512 contiguous bytes (row-major partials were 32 half-filled sectors per
+          // store: 3.5 us for a 40 KB tile), and the reducer reads them back with the row index fastest.
+          const int cols4 = g.bn >> 2;
+          const size_t tile4 = static_cast<size_t>(t.m_blk * g.n_tiles3 + t.n) * (cols4 * kBlockM);
+          float4* part = reinterpret_cast<float4*>(a.split_partial) + t.slice * g.split_plane4 + tile4;
           for (int c = 0; c < cpg; c += CH) {
             uint32_t acc[CH];
             tc::tmem_ld_cols<CH>(taddr + c, acc);
             tc::tmem_ld_wait();
-            if (row_ok) {
 #pragma unroll
-              for (int i = 0; i < CH; i += 4)
-                if (c + i < nvalid)
-                  __stcg(reinterpret_cast<float4*>(part + c + i),
-                         make_float4(__uint_as_float(acc[i]), __uint_as_float(acc[i + 1]), __uint_as_float(acc[i + 2]),
-                                     __uint_as_float(acc[i + 3])));
-            }
+            for (int i = 0; i < CH; i += 4)
+              __stcg(part + ((col0 + c + i) >> 2) * kBlockM + q_row,
+                     make_float4(__uint_as_float(acc[i]), __uint_as_float(acc[i + 1]), __uint_as_float(acc[i + 2]),
+                                 __uint_as_float(acc[i + 3])));
           }
           tc::fence_before_thread_sync();
           __syncwarp();
           if (lane == 0) tc::mbar_arrive_cluster(tc::mapa_u32(&bars->tmem_empty[as], 0));
+#if MOE_TRACE
+          if (ew == 0 && lane == 0 && it == 0) TRACE(48);
+#endif
           // all partial stores of the CTA, then ONE releasing increment: it publishes this slice's partial tile; the
           // last slice to arrive reads the other slices' tiles from L2 (ld.cg) after the barrier below
           tc::named_bar_sync(1, kEpiThreads);
@@ -1208,31 +1213,61 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             bars->last_cta = last;
           }
           tc::named_bar_sync(1, kEpiThreads);
+#if MOE_TRACE
+          if (ew == 0 && lane == 0 && it == 0) TRACE(49);
+#endif
           if (bars->last_cta) {
-            const int et = ew * 32 + lane;
-            const int cols4 = g.bn >> 2;
+            // sum the slices (row index fastest: coalesced 16-byte loads), add b2, and stage the bf16 tile in the
+            // swizzled staging layout; one thread then TMA-stores it (clipped at T rows / d columns)
+            if (use[0] > 0) tc::mbar_wait(&bars->hs_empty[0], (use[0] - 1) & 1u);   // phase-1 stores have left the buffers
+            if (use[1] > 0) tc::mbar_wait(&bars->hs_empty[1], (use[1] - 1) & 1u);
+            const uint32_t ybase = tc::smem_u32(hstage);
+            const float4* src = reinterpret_cast<const float4*>(a.split_partial) + tile4;
             const int tile_col0 = t.n * g.bn;
-            const int tile_row0 = t.m_blk * kBlockM;
-            for (int e = et; e < kBlockM * cols4; e += kEpiThreads) {
-              const int r = e / cols4, c4 = (e - r * cols4) << 2;
-              const int grow = tile_row0 + r, gcol = tile_col0 + c4;
-              if (grow >= g.T || gcol >= g.d) continue;
-              const float* src = a.split_partial + static_cast<size_t>(grow) * g.d + gcol;
-              float4 pz[8];
+            // five chunks per thread and trip, the first two slices of all of them in flight together (one L2 round
+            // trip per trip instead of one per chunk); further slices are added in order afterwards
+            constexpr int kU = 5;
+            const int total = kBlockM * cols4;
+            for (int e0 = ew * 32 + lane; e0 < total; e0 += kU * kEpiThreads) {
+              float4 p0[kU], p1[kU];
 #pragma unroll
-              for (int sl = 0; sl < 8; ++sl)
-                if (sl < g.split3) pz[sl] = __ldcg(reinterpret_cast<const float4*>(src + sl * plane));
-              float4 sum = a.b2 != nullptr ? __ldg(reinterpret_cast<const float4*>(a.b2 + gcol)) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-              for (int sl = 0; sl < 8; ++sl)
-                if (sl < g.split3) {
-                  sum.x += pz[sl].x;
-                  sum.y += pz[sl].y;
-                  sum.z += pz[sl].z;
-                  sum.w += pz[sl].w;
+              for (int u = 0; u < kU; ++u) {
+                const int e = e0 + u * kEpiThreads;
+                p0[u] = p1[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (e < total) {
+                  const float4* q = src + (e >> 7) * kBlockM + (e & (kBlockM - 1));
+                  p0[u] = __ldcg(q);
+                  if (g.split3 > 1) p1[u] = __ldcg(q + g.split_plane4);
                 }
-              *reinterpret_cast<uint2*>(a.Y + static_cast<size_t>(grow) * g.d + gcol) =
-                  make_uint2(pack_bf16x2(sum.x, sum.y), pack_bf16x2(sum.z, sum.w));
+              }
+#pragma unroll
+              for (int u = 0; u < kU; ++u) {
+                const int e = e0 + u * kEpiThreads;
+                if (e >= total) break;
+                const int r = e & (kBlockM - 1), c4i = e >> 7;
+                const int gcol = tile_col0 + 4 * c4i;
+                float4 sum = (a.b2 != nullptr && gcol < g.d) ? __ldg(reinterpret_cast<const float4*>(a.b2 + gcol))
+                                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+                sum.x += p0[u].x; sum.y += p0[u].y; sum.z += p0[u].z; sum.w += p0[u].w;     // slice order: deterministic
+                sum.x += p1[u].x; sum.y += p1[u].y; sum.z += p1[u].z; sum.w += p1[u].w;
+                for (int sl = 2; sl < g.split3; ++sl) {
+                  const float4 v = __ldcg(src + sl * g.split_plane4 + c4i * kBlockM + r);
+                  sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+                }
+                tc::sts_b32x2(stage_addr(ybase, hl3, r, 4 * c4i), pack_bf16x2(sum.x, sum.y), pack_bf16x2(sum.z, sum.w));
+              }
+            }
+            tc::fence_proxy_async_smem();
+            tc::named_bar_sync(1, kEpiThreads);
+            if (ew == 0 && lane == 0) {
+              const int n_full = g.bn >> 6;
+              for (int pn = 0; pn < n_full; ++pn)
+                if (tile_col0 + 64 * pn < g.d)
+                  tc::tma_store_2d(&tmap_y, hstage + pn * (kBlockM * 128), tile_col0 + 64 * pn, t.m_blk * kBlockM);
+              if ((g.bn & 63) && tile_col0 + 64 * n_full < g.d)
+                tc::tma_store_2d(&tmap_y_rem, hstage + n_full * (kBlockM * 128), tile_col0 + 64 * n_full, t.m_blk * kBlockM);
+              tc::tma_store_commit();
+              tc::tma_store_wait_read<0>();   // the staging area is free again (and may be reused by the next item)
             }
           }
           tc::named_bar_sync(1, kEpiThreads);
@@ -1287,7 +1322,10 @@ extern "C" {
 size_t moe_ffn_fused_workspace_bytes(int T, int d, int h) {
   using namespace moe::fused;
   (void)h;
-  size_t want = static_cast<size_t>(8) * static_cast<size_t>(T > 0 ? T : 0) * static_cast<size_t>(d > 0 ? d : 0) * 4;
+  // up to 8 K slices of fp32 partial tiles: whole 256-row units x whole column tiles (at most 256 wide)
+  const size_t rows = (static_cast<size_t>(T > 0 ? T : 0) + 255) / 256 * 256;
+  const size_t cols = static_cast<size_t>(d > 0 ? d : 0) + 256;   // >= ceil(d / bn) * bn for every tile width bn <= 256
+  size_t want = static_cast<size_t>(8) * rows * cols * 4;
   const size_t cap = static_cast<size_t>(64) << 20;
   if (want > cap) want = cap;
   return kSyncBytes + kSplitCounterBytes + want;
@@ -1385,7 +1423,7 @@ int moe_ffn_fused(const void* x, const void* w1p, const float* b1p, const void* 
   g.nkb3 = h / kBlockK;
   size_t max_split_ws = 1;
   {
-    const size_t per_slice = static_cast<size_t>(T) * d * 4;
+    const size_t per_slice = (static_cast<size_t>(T) + 255) / 256 * 256 * (static_cast<size_t>(d) + 256) * 4;
     const size_t avail = workspace_bytes - kSyncBytes - kSplitCounterBytes;
     max_split_ws = per_slice ? avail / per_slice : 1;
     if (max_split_ws > 8) max_split_ws = 8;
@@ -1457,6 +1495,7 @@ int moe_ffn_fused(const void* x, const void* w1p, const float* b1p, const void* 
   g.kb_per_slice3 = (g.kb_per_slice3 + g.ks3 - 1) / g.ks3 * g.ks3;
   while (g.split3 > 1 && (g.split3 - 1) * g.kb_per_slice3 >= g.nkb3) --g.split3;
   g.items3 = g.m_pairs * g.n_tiles3 * g.split3;
+  g.split_plane4 = static_cast<long long>(2 * g.m_pairs) * g.n_tiles3 * (g.bn / 4) * kBlockM;
 
   // ---- routing geometry: L lanes per token (chunk = 512 / L tokens, L / 4 chunks per 128-row block).  The
   // block's `consumers` phase-3 items share its chunks, so few consumers want large chunks; each lane holds
