@@ -1452,7 +1452,7 @@ int moe_ffn_fused(const void* x, const void* w1p, const float* b1p, const void* 
       const long long items = static_cast<long long>(g.m_pairs) * n_tiles_c * sp;
       const long long rounds = (items + P - 1) / P;
       const double per_kblock = 115.0 + (2.0 * bn > 220.0 ? 2.0 * bn : 220.0);
-      const double cost = rounds * (kb_per * per_kblock + 2500.0) + (sp > 1 ? 6000.0 + 40.0 * sp * bn : 0.0);
+      const double cost = rounds * (kb_per * per_kblock + 2500.0) + (sp > 1 ? 3000.0 + 20.0 * sp * bn : 0.0);
       if (cost < best_cost * 0.999) {
         best_cost = cost;
         best_bn = bn;
