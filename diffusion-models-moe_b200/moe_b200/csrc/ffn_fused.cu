@@ -112,10 +112,13 @@ struct Shape {
   int chunk_tokens, chunks_per_block;           // chunk = route_warps * 32 / lanes tokens = one pass of those warps
   int words;                                    // expert-set words per token
   int act, mask_h, count_begin, count_end;
+  int prefetch_weights;
   uint32_t es_magic;
 };
 
 struct Ptrs {
+  const void* w1;           // raw weight pointers, only for the L2 prefetch before the dependency wait
+  const void* w2;
   const float* b1;
   const float* b2;
   float* scores;
@@ -776,6 +779,21 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   tc::cluster_sync_all();
   tc::fence_after_thread_sync();
   if (threadIdx.x == 0) TRACE(1);
+  // The weights do not depend on the previous kernel: while this CTA waits for it (CTAs of this grid become resident
+  // as the predecessor's CTAs exit, up to ~20 us before its last one), pull this CTA's share of W1 and W2 into L2.
+  if (warp == 3 && lane == 0 && g.prefetch_weights) {
+    const size_t n1 = static_cast<size_t>(2) * g.h * g.d * 2, n2 = static_cast<size_t>(g.d) * g.h * 2;
+    const size_t piece = 16384;
+    const size_t pieces1 = (n1 + piece - 1) / piece, pieces2 = (n2 + piece - 1) / piece;
+    for (size_t i = blockIdx.x; i < pieces1 + pieces2; i += gridDim.x) {
+      const bool first = i < pieces1;
+      const size_t off = (first ? i : i - pieces1) * piece;
+      const size_t left = (first ? n1 : n2) - off;
+      const uint32_t bytes = static_cast<uint32_t>(left < piece ? left : piece) & ~15u;
+      const char* src = static_cast<const char*>(first ? a.w1 : a.w2) + off;
+      if (bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+    }
+  }
   pdl_wait();   // everything above overlapped the previous kernel's tail
   if (threadIdx.x == 0) pdl_launch_dependents();
   if (threadIdx.x == 0) TRACE(2);
@@ -1539,6 +1557,8 @@ int moe_ffn_fused(const void* x, const void* w1p, const float* b1p, const void* 
   g.count_begin = count_begin;
   g.count_end = count_end;
   g.es_magic = static_cast<uint32_t>((0x100000000ull / static_cast<unsigned>(es)) + 1ull);
+  g.prefetch_weights = 1;
+  if (const char* e = getenv("MOE_FUSED_PREFETCH")) g.prefetch_weights = atoi(e) != 0;
 
   if (getenv("MOE_DEBUG_PRINT"))
     fprintf(stderr,
@@ -1573,6 +1593,8 @@ int moe_ffn_fused(const void* x, const void* w1p, const float* b1p, const void* 
     return rc;
 
   Ptrs a = {};
+  a.w1 = w1p;
+  a.w2 = w2p;
   a.b1 = b1p;
   a.b2 = b2;
   a.scores = scores;
