@@ -13,7 +13,8 @@ states and random-init weights of the SD-1.5 geometry.
             inputs resident in HBM, the step replayed as one CUDA graph; time = CUDA events, max over ranks.
   e2e       same metric with HOST buffers: per step the 16 layer inputs are copied from pinned host memory,
             the FFNs run through the C ABI, outputs + histogram are copied back (all inside the timing); copy-in,
-            compute and copy-out run on three streams chained per layer.
+            compute and copy-out run on three streams chained per layer, consecutive steps pipelined (PCIe-bound:
+            tools/pcie_probe.py measures the two-direction copy ceiling for the same bytes).
   roofline  dominant kernel (ffn_fused_kernel): algorithmic FLOPs (6 d h per token) / CUDA-event time of its launches.
   cpu_baseline  the oracle port of the reference's hook arithmetic (fp32 torch-CPU, all host threads), timed
             here on rank 0 at N=1 on a bounded sample (one layer per distinct shape x multiplicity).
@@ -63,6 +64,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=2, help="UNet batch (2 = one prompt with CFG)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--e2e-groups", type=int, default=2, help="copy groups per step in the e2e leg (1..16)")
     ap.add_argument("--path", default="fused", choices=["fused", "split"],
                     help="fused: one moe_ffn_fused launch per layer; split: K1 -> K2 -> K3 launches")
     return ap.parse_args()
@@ -182,31 +184,49 @@ def gpu_arm(args):
         w2 = ((torch.rand(d, h, generator=wgen) * 2 - 1) / h ** 0.5)
         b2 = ((torch.rand(d, generator=wgen) * 2 - 1) / h ** 0.5)
         p = pack_ffn(ExpertLayout.contiguous(E, es), w1, b1, w2, b2, device=dev)
-        x_host = torch.nn.functional.layer_norm(torch.randn(B * s, d, generator=gen), (d,)).to(torch.bfloat16).pin_memory()
+        x_host = torch.nn.functional.layer_norm(torch.randn(B * s, d, generator=gen), (d,)).to(torch.bfloat16)
         T = B * s
         layers.append(dict(d=d, h=h, s=s, T=T, E=E, es=es, k=int(E * RATIO), p=p, x_host=x_host,
                            x=x_host.to(dev), H=torch.empty(T, h, dtype=torch.bfloat16, device=dev),
                            scores=torch.empty(T, E, dtype=torch.float32, device=dev),
-                           y=torch.empty(T, d, dtype=torch.bfloat16, device=dev),
-                           y_host=torch.empty(T, d, dtype=torch.bfloat16).pin_memory()))
+                           y=torch.empty(T, d, dtype=torch.bfloat16, device=dev)))
+    # host side of the e2e leg: one pinned arena per direction, the per-layer host buffers are views into it; on the
+    # device two copies of each arena (step parity) so that a step's copy-in never waits for the previous step
+    n_elem = sum(L["T"] * L["d"] for L in layers)
+    x_arena_host = torch.empty(n_elem, dtype=torch.bfloat16).pin_memory()
+    y_arena_host = torch.empty(n_elem, dtype=torch.bfloat16).pin_memory()
+    x_arena = [torch.empty(n_elem, dtype=torch.bfloat16, device=dev) for _ in range(2)]
+    y_arena = [torch.empty(n_elem, dtype=torch.bfloat16, device=dev) for _ in range(2)]
+    off = 0
+    for L in layers:
+        n = L["T"] * L["d"]
+        L["off"], L["n"] = off, n
+        x_arena_host[off:off + n].copy_(L["x_host"].reshape(-1))
+        L["x_host"] = x_arena_host[off:off + n].view(L["T"], L["d"])
+        L["y_host"] = y_arena_host[off:off + n].view(L["T"], L["d"])
+        L["x2"] = [a[off:off + n].view(L["T"], L["d"]) for a in x_arena]
+        L["y2"] = [a[off:off + n].view(L["T"], L["d"]) for a in y_arena]
+        off += n
     hist = torch.zeros(len(layers), e_max, dtype=torch.int64, device=dev)
     hist_host = torch.zeros(len(layers), e_max, dtype=torch.int64).pin_memory()
     tokens_per_step = sum(L["T"] for L in layers)
 
     fused = args.path == "fused"
 
-    def layer_call(li):
+    def layer_call(li, x=None, y=None):
         """One hooked FFN layer call on the current stream: fused kernel, or the K1 -> K2 -> K3 triple."""
         L = layers[li]
         p = L["p"]
+        x = L["x"] if x is None else x
+        y = L["y"] if y is None else y
         if fused:
-            M.ffn_fused(L["x"], p.w1p, p.b1p, p.w2p, p.b2, L["E"], L["es"], L["k"], M.ACT_GELU,
-                        hist=hist[li, :L["E"]], count_rows=(0, L["s"]), H_out=L["H"], scores_out=L["scores"], out=L["y"])
+            M.ffn_fused(x, p.w1p, p.b1p, p.w2p, p.b2, L["E"], L["es"], L["k"], M.ACT_GELU,
+                        hist=hist[li, :L["E"]], count_rows=(0, L["s"]), H_out=L["H"], scores_out=L["scores"], out=y)
             return
-        M.geglu_up(L["x"], p.w1p, p.b1p, L["E"], L["es"], M.ACT_GELU, out=L["H"], scores_out=L["scores"])
+        M.geglu_up(x, p.w1p, p.b1p, L["E"], L["es"], M.ACT_GELU, out=L["H"], scores_out=L["scores"])
         M.router_topk(L["scores"], L["k"], want_bits=False, hist=hist[li, :L["E"]], H=L["H"], expert_size=L["es"],
                       count_rows=(0, L["s"]))
-        M.down_proj(L["H"], p.w2p, p.b2, out=L["y"])
+        M.down_proj(L["H"], p.w2p, p.b2, out=y)
 
     def ffn_step():
         for li in range(len(layers)):
@@ -308,61 +328,85 @@ def gpu_arm(args):
     h2d = sum(L["x_host"].numel() * 2 for L in layers)
     d2h = sum(L["y_host"].numel() * 2 for L in layers) + hist_host.numel() * 8
 
-    # Three streams, one per direction, chained per layer with events: the copy-in of layer l+1 and the copy-out of
-    # layer l-1 run on the two DMA engines while layer l computes; steps are serialised.
+    # Three streams: copy-in, compute, copy-out.  Each step's layers are cut into --e2e-groups contiguous groups of
+    # about equal bytes; a group is copied in with one DMA (host arena slice -> device arena slice), its layers run as
+    # soon as it has landed, and its outputs go back with one DMA, so copy-in of group g+1 and copy-out of group g-1
+    # overlap the kernels of group g.  Consecutive steps alternate between two device arenas, so the copy-in of step
+    # s+1 overlaps the tail of step s; a device arena slice is reused only after the step-before-last's kernels /
+    # copy-out that touch it have finished (events below).  Every step copies all inputs in and all results out.
     s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
     nL = len(layers)
+    n_groups = max(1, min(args.e2e_groups, nL))
+    groups, acc, cur = [], 0, []
+    for li, L in enumerate(layers):
+        cur.append(li)
+        acc += L["n"]
+        if acc >= n_elem * (len(groups) + 1) / n_groups or li == nL - 1:
+            groups.append(cur)
+            cur = []
+    groups = [g for g in groups if g]
 
-    def e2e_step(main):
-        """One step with host buffers on three streams forked from / joined into `main`."""
-        ev_in = [torch.cuda.Event() for _ in range(nL)]
-        ev_cmp = [torch.cuda.Event() for _ in range(nL)]
+    def e2e_steps(main, n):
+        """n steps with host buffers on three streams forked from / joined into `main`."""
         s_in.wait_stream(main)
         s_out.wait_stream(main)
-        for li, L in enumerate(layers):
-            with torch.cuda.stream(s_in):
-                L["x"].copy_(L["x_host"], non_blocking=True)
-                ev_in[li].record(s_in)
-            main.wait_event(ev_in[li])
-            layer_call(li)
-            ev_cmp[li].record(main)
+        ev_cmp = {}       # (parity, group) -> kernels of that group done in the last step of that parity
+        ev_out = {}       # (parity, group) -> copy-out of that group's outputs done
+        for step in range(n):
+            par = step & 1
+            for gi, g in enumerate(groups):
+                lo, hi = layers[g[0]]["off"], layers[g[-1]]["off"] + layers[g[-1]]["n"]
+                ev_in = torch.cuda.Event()
+                with torch.cuda.stream(s_in):
+                    if (par, gi) in ev_cmp:
+                        s_in.wait_event(ev_cmp[(par, gi)])
+                    x_arena[par][lo:hi].copy_(x_arena_host[lo:hi], non_blocking=True)
+                    ev_in.record(s_in)
+                main.wait_event(ev_in)
+                if (par, gi) in ev_out:
+                    main.wait_event(ev_out[(par, gi)])
+                for li in g:
+                    layer_call(li, layers[li]["x2"][par], layers[li]["y2"][par])
+                ev_cmp[(par, gi)] = torch.cuda.Event()
+                ev_cmp[(par, gi)].record(main)
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(ev_cmp[(par, gi)])
+                    y_arena_host[lo:hi].copy_(y_arena[par][lo:hi], non_blocking=True)
+                    ev_out[(par, gi)] = torch.cuda.Event()
+                    ev_out[(par, gi)].record(s_out)
             with torch.cuda.stream(s_out):
-                s_out.wait_event(ev_cmp[li])
-                L["y_host"].copy_(L["y"], non_blocking=True)
-        with torch.cuda.stream(s_out):
-            hist_host.copy_(hist, non_blocking=True)
+                hist_host.copy_(hist, non_blocking=True)
         main.wait_stream(s_in)
-        main.wait_stream(s_out)       # the step's results (outputs + histogram) are on the host
+        main.wait_stream(s_out)       # every step's results (outputs + histogram) are on the host
 
-    for _ in range(3):
-        e2e_step(torch.cuda.current_stream())
+    n_e2e = min(args.steps, 20)
+    e2e_steps(torch.cuda.current_stream(), 3)
     torch.cuda.synchronize()
     e2e_graph = None
     if not args.no_graph:
-        # the same step as one CUDA graph (copies included), so that the 16 x (2 copies + launch) per step are not
-        # paced by the Python / ctypes host path
+        # the same n_e2e steps as one CUDA graph (copies included), so that the 16 x (2 copies + launch) per step are
+        # not paced by the Python / ctypes host path
         e2e_graph = torch.cuda.CUDAGraph()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             with torch.cuda.graph(e2e_graph, stream=side):
-                e2e_step(side)
+                e2e_steps(side, n_e2e)
         torch.cuda.current_stream().wait_stream(side)
-        for _ in range(3):
+        for _ in range(2):
             e2e_graph.replay()
     barrier()
-    n_e2e = min(args.steps, 20)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(n_e2e):
-        if e2e_graph is not None:
-            e2e_graph.replay()
-        else:
-            e2e_step(torch.cuda.current_stream())
+    if e2e_graph is not None:
+        e2e_graph.replay()
+    else:
+        e2e_steps(torch.cuda.current_stream(), n_e2e)
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1) / n_e2e
-    y_check = float(layers[0]["y_host"].float().abs().sum())      # the copied-back result is real data
+    y_check = float(layers[0]["y_host"].float().abs().sum())      # the copied-back result is real data ...
+    e2e_same = all(torch.equal(L["y_host"], L["y"].cpu()) for L in layers)   # ... and equals the resident-input run's
 
     clocks = sampler.stop() if rank == 0 else None   # sampled across the timed region, the breakdown and e2e
     stats = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
@@ -423,7 +467,8 @@ def gpu_arm(args):
                 unet_steps_per_s=world * 1e3 / ms_step,
                 e2e=dict(value=world * tokens_per_step / (ms_e2e * 1e-3), unit="tokens/s", h2d_bytes_per_step=h2d,
                          d2h_bytes_per_step=d2h, ms_per_step=ms_e2e, cuda_graph=e2e_graph is not None,
-                         output_abs_sum_layer0=y_check),
+                         copies_per_step=2 * len(groups) + 1, pipelined_steps=True,
+                         output_abs_sum_layer0=y_check, outputs_equal_resident_run=e2e_same),
                 gpu_launches=launches_per_step * args.steps, clocks=clocks, roofline=roofline,
                 histogram_counts_exact=counts_ok)
     if world == 1 and not args.no_cpu_baseline:
