@@ -210,20 +210,21 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&p);
 }
 
-// exact-erf GELU of two values: x Phi(x) = max(x, 0) - |x| * 0.5 erfc(|x| / sqrt 2), 0.5 erfc(t) = 2^P7(t) for
-// t = min(|x| / sqrt 2, 4.3) (weighted minimax fit, max abs error 4e-7 on [-3, 3]); the polynomial runs as seven
-// packed FFMA2, the rest is one MUFU.EX2 and three scalar ops per value.
+// exact-erf GELU of two values: x Phi(x) = max(x, 0) - |x| * 0.5 erfc(|x| / sqrt 2), 0.5 erfc(u / sqrt 2) = 2^P7(u)
+// for u = min(|x|, 4.3 sqrt 2) (weighted minimax fit, the 1 / sqrt 2 folded into the coefficients; max abs error
+// 4e-7 on [-3, 3]); the polynomial runs as seven packed FFMA2, the rest is one MUFU.EX2 and three scalar ops per value.
+// gemm_tc.cu's gelu_erf evaluates the same expression with scalar FFMAs (bit-identical results).
 __device__ __forceinline__ uint64_t gelu2(float x0, float x1) {
-  const float t0 = fminf(fabsf(x0) * 0.70710678118654752f, 4.3f);
-  const float t1 = fminf(fabsf(x1) * 0.70710678118654752f, 4.3f);
+  const float t0 = fminf(fabsf(x0), 6.081118318204309f);
+  const float t1 = fminf(fabsf(x1), 6.081118318204309f);
   const uint64_t t = pk2(t0, t1);
-  uint64_t q = pk2(1.0664232831913978e-04f, 1.0664232831913978e-04f);
-  q = fma2(q, t, pk2(-5.025442806072533e-04f, -5.025442806072533e-04f));
-  q = fma2(q, t, pk2(-2.20537674613297e-03f, -2.20537674613297e-03f));
-  q = fma2(q, t, pk2(2.9348013922572136e-02f, 2.9348013922572136e-02f));
-  q = fma2(q, t, pk2(-1.4891357719898224e-01f, -1.4891357719898224e-01f));
-  q = fma2(q, t, pk2(-9.183364510536194e-01f, -9.183364510536194e-01f));
-  q = fma2(q, t, pk2(-1.6279140710830688f, -1.6279140710830688f));
+  uint64_t q = pk2(9.425939424545504e-06f, 9.425939424545504e-06f);
+  q = fma2(q, t, pk2(-6.281803507590666e-05f, -6.281803507590666e-05f));
+  q = fma2(q, t, pk2(-3.898592258337885e-04f, -3.898592258337885e-04f));
+  q = fma2(q, t, pk2(7.337003480643034e-03f, 7.337003480643034e-03f));
+  q = fma2(q, t, pk2(-5.264890193939209e-02f, -5.264890193939209e-02f));
+  q = fma2(q, t, pk2(-4.591682255268097e-01f, -4.591682255268097e-01f));
+  q = fma2(q, t, pk2(-1.1511090993881226f, -1.1511090993881226f));
   q = fma2(q, t, pk2(-0.9999999403953552f, -0.9999999403953552f));
   float q0, q1;
   unpk2(q, q0, q1);
@@ -648,9 +649,9 @@ __device__ __forceinline__ void stage_store(uint32_t base, const StageLayout& l,
 
 // the same with the pieces' byte offsets computed once per kernel (they depend on the thread's row and column group
 // only): `off[i]` = offset of 4-column piece i of the chunk; `aligned` = the chunk starts on an 8-column boundary
-template <int kWords>
-__device__ __forceinline__ void stage_store_pre(uint32_t base, const uint32_t* off, bool aligned, const uint32_t* w) {
-  if (aligned) {
+template <int kWords, bool aligned>
+__device__ __forceinline__ void stage_store_pre(uint32_t base, const uint32_t* off, const uint32_t* w) {
+  if constexpr (aligned) {
 #pragma unroll
     for (int i = 0; i + 4 <= kWords; i += 4) tc::sts_b32x4(base + off[i / 2], w[i], w[i + 1], w[i + 2], w[i + 3]);
     if constexpr (kWords % 4 != 0) tc::sts_b32x2(base + off[kWords / 2 - 1], w[kWords - 2], w[kWords - 1]);
@@ -662,23 +663,42 @@ __device__ __forceinline__ void stage_store_pre(uint32_t base, const uint32_t* o
   }
 }
 
-template <int CH, int ACT>
-__device__ __forceinline__ void geglu_group(const Shape& g, uint32_t taddr, const float* sbias, uint32_t hbase,
-                                            const uint32_t* piece_off, bool aligned, float* spart_row, float* score_dst,
-                                            int col0, int cpg, int cg) {
+// store one score to global memory under a predicate, without a branch (a per-thread `if` around the store costs a
+// BSSY / BSYNC pair per expert in the epilogue's inner loop)
+__device__ __forceinline__ void st_global_if(float* p, float v, bool pred) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q st.global.f32 [%0], %1;\n\t}" ::"l"(p), "f"(v),
+               "r"(static_cast<int>(pred))
+               : "memory");
+}
+
+// One thread's share of a phase-1 tile: row q_row, the cpg (<= 32) value columns of its column group and the matching
+// gate columns, CH columns at a time.  The chunk loop is unrolled over its compile-time maximum, so the staging
+// offsets stay in registers; everything that does not change from tile to tile is computed by the caller.
+//   taddr_v / taddr_g  TMEM address of the group's first value / gate column (this warp's lane quarter)
+//   cpe                chunks per expert when whole experts lie inside a column group, else 0
+//   score_dst          global slot of the group's first expert score for this row (stored only if score_ok)
+//   spart_slot         shared-memory slot of this group's partial sum (experts that span column groups)
+template <int CH, int ACT, bool kAligned>
+__device__ __forceinline__ void geglu_group(uint32_t taddr_v, uint32_t taddr_g, const float* sbias, uint32_t hbase,
+                                            const uint32_t (&piece_off)[8], float* spart_slot,
+                                            float* score_dst, bool score_ok, int cpg, int cpe) {
   uint64_t score2 = pk2(0.f, 0.f);
-  int chunk_in_expert = 0, e_slot = (g.chunks_per_expert > 0) ? cg * (cpg / g.es) : cg;
-  // the chunk's TMEM loads are split in two: the second half is in flight while the first half is processed
+  int chunk_in_expert = 0;
+  // a chunk's TMEM loads are split in two: the second half is in flight while the first half is processed
   // (TMEM reads run at ~16 B/clk per lane quarter -- a whole tile takes ~1300 cycles to read out)
   constexpr int kA = (CH >= 8) ? (CH / 2) / 4 * 4 : CH;
-  for (int c = 0; c < cpg; c += CH) {
+  constexpr int kMaxChunks = 32 / CH;
+#pragma unroll
+  for (int ci = 0; ci < kMaxChunks; ++ci) {
+    const int c = ci * CH;
+    if (ci > 0 && c >= cpg) break;
     uint32_t v[CH], gt[CH];
-    tc::tmem_ld_cols<kA>(taddr + col0 + c, v);
-    tc::tmem_ld_cols<kA>(taddr + g.nv + col0 + c, gt);
+    tc::tmem_ld_cols<kA>(taddr_v + c, v);
+    tc::tmem_ld_cols<kA>(taddr_g + c, gt);
     tc::tmem_ld_wait();
     if constexpr (kA < CH) {
-      tc::tmem_ld_cols<CH - kA>(taddr + col0 + c + kA, v + kA);
-      tc::tmem_ld_cols<CH - kA>(taddr + g.nv + col0 + c + kA, gt + kA);
+      tc::tmem_ld_cols<CH - kA>(taddr_v + c + kA, v + kA);
+      tc::tmem_ld_cols<CH - kA>(taddr_g + c + kA, gt + kA);
     }
     uint32_t hw[CH / 2];
 #pragma unroll
@@ -702,22 +722,21 @@ __device__ __forceinline__ void geglu_group(const Shape& g, uint32_t taddr, cons
       hw[i / 2] = pack_bf16x2(h0, h1);
       hw[i / 2 + 1] = pack_bf16x2(h2, h3);
     }
-    stage_store_pre<CH / 2>(hbase, piece_off + c / 4, aligned, hw);
-    if (g.chunks_per_expert > 0 && ++chunk_in_expert == g.chunks_per_expert) {
+    stage_store_pre<CH / 2, kAligned>(hbase, &piece_off[(ci * CH) / 4], hw);
+    if (cpe > 0 && ++chunk_in_expert == cpe) {
       float s0, s1;
       unpk2(score2, s0, s1);
       // whole expert inside this thread's column group: its score goes straight to global memory
-      // (score_dst = this row's slice of the tile's experts, or null beyond T)
-      if (score_dst != nullptr) score_dst[e_slot] = s0 + s1;
-      ++e_slot;
+      st_global_if(score_dst, s0 + s1, score_ok);
+      ++score_dst;
       score2 = pk2(0.f, 0.f);
       chunk_in_expert = 0;
     }
   }
-  if (g.chunks_per_expert == 0) {
+  if (cpe == 0) {
     float s0, s1;
     unpk2(score2, s0, s1);
-    spart_row[cg] = s0 + s1;
+    *spart_slot = s0 + s1;
   }
 }
 
@@ -1052,7 +1071,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     uint32_t* s_words = s_words_all + ew * 16;
     const int q_row = 32 * q + lane;
     int acc_it = 0;
-    int use[2] = {0, 0};
+    int use0 = 0, use1 = 0;     // uses of the two staging buffers so far
     Item t;
     const StageLayout hl1 = stage_layout(g.nv), hl3 = stage_layout(g.bn);
     // ---------------------------------------------------------------- phase 1
@@ -1061,82 +1080,95 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       const int col0 = cg * cpg;
       // per-thread constants of the loop: byte offsets of this thread's 4-column pieces inside a staging buffer
       // (row q_row, columns col0 ...) and whether the column group starts on an 8-column boundary
-      uint32_t piece_off[16];
+      uint32_t piece_off[8];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) piece_off[i] = (4 * i < cpg) ? stage_addr(0u, hl1, q_row, col0 + 4 * i) : 0u;
+      for (int i = 0; i < 8; ++i) piece_off[i] = (4 * i < cpg) ? stage_addr(0u, hl1, q_row, col0 + 4 * i) : 0u;
       const bool aligned = ((col0 | CH) & 7) == 0 || (col0 & 7) == 0;
+      // tile-invariant pieces of the epilogue's addresses: the group's first expert inside a tile, this row's score
+      // slot relative to the tile, the TMEM columns of the group
+      const int cpe = g.chunks_per_expert;
+      const int e_slot0 = (cpe > 0) ? cg * (cpg / g.es) : cg;
+      const int act = g.act;
+      const int n_items1 = g.items1, n_tiles1 = g.n_tiles1, step_m1 = g.step_m1, step_n1 = g.step_n1;
+      const long long score_row_stride = static_cast<long long>(kBlockM) * g.E;
+      float* const score_row0 = a.scores + static_cast<long long>(rm * kBlockM + q_row) * g.E + e_slot0;
+      const int experts_per_tile = g.experts_per_tile;
+      const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + col0;
+      const uint32_t hbase0 = tc::smem_u32(hstage);
+      const uint32_t hs_bytes = g.hs_bytes;
+      const int nv = g.nv;
+      const int rows_left0 = g.T - (rm * kBlockM + q_row);   // this row is inside the matrix iff rows_left0 > 256 mp
       // tile coordinates advance by a fixed step per iteration: no divisions in the loop
-      int i1 = p, mp1 = p / g.n_tiles1, n1 = p - (p / g.n_tiles1) * g.n_tiles1;
+      int i1 = p, mp1 = p / n_tiles1, n1 = p - (p / n_tiles1) * n_tiles1;
       // bias slices: the first tile's are staged up front, every later tile's are fetched into registers while
       // the previous tile is being processed (a staged load per tile exposed ~0.8 us of global latency each time)
-      if (i1 < g.items1)
-        stage_bias(sbias, a.b1 != nullptr ? a.b1 + n1 * g.nv + col0 : nullptr,
-                   a.b1 != nullptr ? a.b1 + g.h + n1 * g.nv + col0 : nullptr, cpg, lane);
-      for (int it = 0; i1 < g.items1; ++it, ++acc_it) {
-        t.m_blk = 2 * mp1 + rm;
-        t.n = n1;
+      if (i1 < n_items1)
+        stage_bias(sbias, a.b1 != nullptr ? a.b1 + n1 * nv + col0 : nullptr,
+                   a.b1 != nullptr ? a.b1 + g.h + n1 * nv + col0 : nullptr, cpg, lane);
+      int it = 0;
+      for (; i1 < n_items1; ++it, ++acc_it) {
+        const int mp_cur = mp1, n_cur = n1;
         // next tile of this pair
         i1 += P;
-        mp1 += g.step_m1;
-        n1 += g.step_n1;
-        if (n1 >= g.n_tiles1) {
-          n1 -= g.n_tiles1;
+        mp1 += step_m1;
+        n1 += step_n1;
+        if (n1 >= n_tiles1) {
+          n1 -= n_tiles1;
           ++mp1;
         }
         const int as = acc_it & 1;
         const int buf = it & 1;
-        float nb[4] = {0.f, 0.f, 0.f, 0.f};
-        const bool has_next = i1 < g.items1;
-        if (has_next && a.b1 != nullptr) {
-          const float* bv = a.b1 + n1 * g.nv + col0;
-          const float* bg = bv + g.h;
-          if (lane < cpg) {
-            nb[0] = __ldg(bv + lane);
-            nb[2] = __ldg(bg + lane);
-          }
-          if (lane + 32 < cpg) {
-            nb[1] = __ldg(bv + lane + 32);
-            nb[3] = __ldg(bg + lane + 32);
-          }
+        const int ub = it >> 1;          // earlier uses of this staging buffer
+        float nb0 = 0.f, nb2 = 0.f;
+        const bool has_next = i1 < n_items1;
+        if (has_next && a.b1 != nullptr && lane < cpg) {
+          const float* bv = a.b1 + n1 * nv + col0;
+          nb0 = __ldg(bv + lane);
+          nb2 = __ldg(bv + g.h + lane);
         }
-        if (use[buf] > 0) tc::mbar_wait(&bars->hs_empty[buf], (use[buf] - 1) & 1u);   // staging buffer drained
+        if (ub > 0) tc::mbar_wait(&bars->hs_empty[buf], (ub - 1) & 1u);   // staging buffer drained
         tc::mbar_wait(&bars->tmem_full[as], (acc_it >> 1) & 1u);
         tc::fence_after_thread_sync();
 #if MOE_TRACE
         if (ew == 0 && lane == 0 && acc_it < 13) TRACE(8 + 4 * acc_it + 1);
 #endif
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + as * kAccStride;
-        const uint32_t hbase = tc::smem_u32(hstage + buf * g.hs_bytes);
-        float* spart_row = spart + (buf * kBlockM + q_row) * kSpartPerRow;
-        const int row = t.m_blk * kBlockM + q_row;
-        float* score_dst = row < g.T ? a.scores + static_cast<size_t>(row) * g.E + t.n * g.experts_per_tile : nullptr;
-        if (g.act == MOE_ACT_GELU)
-          geglu_group<CH, MOE_ACT_GELU>(g, taddr, sbias, hbase, piece_off, aligned, spart_row, score_dst, col0, cpg, cg);
+        const uint32_t taddr = taddr0 + as * kAccStride;
+        const uint32_t hbase = hbase0 + buf * hs_bytes;
+        float* spart_slot = spart + (buf * kBlockM + q_row) * kSpartPerRow + cg;
+        float* score_dst = score_row0 + 2 * mp_cur * score_row_stride + n_cur * experts_per_tile;
+        const bool score_ok = rows_left0 > 2 * kBlockM * mp_cur;
+        // (the alignment of the group's staging stores is warp-uniform: two instantiations, one uniform branch)
+#define MOE_GEGLU_GROUP(ACT_)                                                                                             \
+  do {                                                                                                                    \
+    if (aligned)                                                                                                          \
+      geglu_group<CH, ACT_, true>(taddr, taddr + nv, sbias, hbase, piece_off, spart_slot, score_dst, score_ok, cpg, cpe); \
+    else                                                                                                                  \
+      geglu_group<CH, ACT_, false>(taddr, taddr + nv, sbias, hbase, piece_off, spart_slot, score_dst, score_ok, cpg, cpe); \
+  } while (0)
+        if (act == MOE_ACT_GELU) MOE_GEGLU_GROUP(MOE_ACT_GELU);
 #if MOE_TRACE
-        else if (g.act == 2)
-          geglu_group<CH, 2>(g, taddr, sbias, hbase, piece_off, aligned, spart_row, score_dst, col0, cpg, cg);
+        else if (act == 2) MOE_GEGLU_GROUP(2);
 #endif
-        else
-          geglu_group<CH, MOE_ACT_RELU>(g, taddr, sbias, hbase, piece_off, aligned, spart_row, score_dst, col0, cpg, cg);
+        else MOE_GEGLU_GROUP(MOE_ACT_RELU);
+#undef MOE_GEGLU_GROUP
         // accumulator stage drained -> the leader's MMA thread may overwrite it
         tc::fence_before_thread_sync();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive_cluster(tc::mapa_u32(&bars->tmem_empty[as], 0));
         if (has_next) {   // this warp is done reading the current slices
-          sbias[lane] = nb[0];
-          sbias[lane + 32] = nb[1];
-          sbias[64 + lane] = nb[2];
-          sbias[64 + lane + 32] = nb[3];
+          sbias[lane] = nb0;
+          sbias[64 + lane] = nb2;
         }
         // H tile: generic-proxy smem writes -> async proxy; the sync warp stores it and publishes the tile
         tc::fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&bars->hs_full[buf]);
-        ++use[buf];
 #if MOE_TRACE
         if (ew == 0 && lane == 0 && acc_it < 13) TRACE(8 + 4 * acc_it + 2);
 #endif
       }
+      use0 = (it + 1) >> 1;
+      use1 = it >> 1;
     }
     // ---------------------------------------------------------------- phase 3
     {
@@ -1163,8 +1195,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         stage_bias(sbias, a.b2 != nullptr ? a.b2 + n0 : nullptr, nullptr, nvalid, lane);
         if (g.split3 == 1) {
           // the whole staging area (both phase-1 buffers) holds one Y tile
-          if (use[0] > 0) tc::mbar_wait(&bars->hs_empty[0], (use[0] - 1) & 1u);
-          if (use[1] > 0) tc::mbar_wait(&bars->hs_empty[1], (use[1] - 1) & 1u);
+          if (use0 > 0) tc::mbar_wait(&bars->hs_empty[0], (use0 - 1) & 1u);
+          if (use1 > 0) tc::mbar_wait(&bars->hs_empty[1], (use1 - 1) & 1u);
         }
         tc::mbar_wait(&bars->tmem_full[as], (acc_it >> 1) & 1u);
         tc::fence_after_thread_sync();
@@ -1195,7 +1227,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           tc::fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) tc::mbar_arrive(&bars->hs_full[0]);
-          ++use[0];
+          ++use0;
         } else {
           // ---- split-K: park this slice's fp32 partial tile; the last slice to arrive reduces in slice order.
           // Partial tiles live in a tile-local layout [slice][tile][16-byte column chunk][row]: a thread owns a row, so a
@@ -1237,8 +1269,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           if (bars->last_cta) {
             // sum the slices (row index fastest: coalesced 16-byte loads), add b2, and stage the bf16 tile in the
             // swizzled staging layout; one thread then TMA-stores it (clipped at T rows / d columns)
-            if (use[0] > 0) tc::mbar_wait(&bars->hs_empty[0], (use[0] - 1) & 1u);   // phase-1 stores have left the buffers
-            if (use[1] > 0) tc::mbar_wait(&bars->hs_empty[1], (use[1] - 1) & 1u);
+            if (use0 > 0) tc::mbar_wait(&bars->hs_empty[0], (use0 - 1) & 1u);   // phase-1 stores have left the buffers
+            if (use1 > 0) tc::mbar_wait(&bars->hs_empty[1], (use1 - 1) & 1u);
             const uint32_t ybase = tc::smem_u32(hstage);
             const float4* src = reinterpret_cast<const float4*>(a.split_partial) + tile4;
             const int tile_col0 = t.n * g.bn;

@@ -83,18 +83,18 @@ __device__ __forceinline__ void trace_at(const GemmShape& g, int slot) {
   if ((g.debug & 32) && blockIdx.x < 256 && slot < 64) g_trace[blockIdx.x * 64 + slot] = tc::global_timer_ns();
 }
 
-// exact GELU x * Phi(x) with Phi from 0.5 * erfc(|x|/sqrt2) = 2^(P7(t)), t = min(|x|/sqrt2, 4.3):
-// branch-free, one MUFU.EX2 + 8 FFMA; max abs error 4e-7 on [-3, 3] (fp32 rounding level; the
-// libdevice erff path costs ~2x the instructions and diverges).  Coefficients: weighted minimax fit.
+// exact GELU x * Phi(x) with Phi from 0.5 * erfc(u / sqrt2) = 2^(P7(u)), u = min(|x|, 4.3 sqrt2) (the 1 / sqrt2 is
+// folded into the coefficients): branch-free, one MUFU.EX2 + 8 FFMA; max abs error 4e-7 on [-3, 3] (fp32 rounding
+// level; the libdevice erff path costs ~2x the instructions and diverges).  Coefficients: weighted minimax fit.
 __device__ __forceinline__ float gelu_erf(float x) {
-  const float t = fminf(fabsf(x) * 0.70710678118654752f, 4.3f);
-  float q = 1.0664232831913978e-04f;
-  q = fmaf(q, t, -5.025442806072533e-04f);
-  q = fmaf(q, t, -2.20537674613297e-03f);
-  q = fmaf(q, t, 2.9348013922572136e-02f);
-  q = fmaf(q, t, -1.4891357719898224e-01f);
-  q = fmaf(q, t, -9.183364510536194e-01f);
-  q = fmaf(q, t, -1.6279140710830688f);
+  const float t = fminf(fabsf(x), 6.081118318204309f);
+  float q = 9.425939424545504e-06f;
+  q = fmaf(q, t, -6.281803507590666e-05f);
+  q = fmaf(q, t, -3.898592258337885e-04f);
+  q = fmaf(q, t, 7.337003480643034e-03f);
+  q = fmaf(q, t, -5.264890193939209e-02f);
+  q = fmaf(q, t, -4.591682255268097e-01f);
+  q = fmaf(q, t, -1.1511090993881226f);
   q = fmaf(q, t, -0.9999999403953552f);
   const float e = tc::ex2_approx(q);               // 0.5 * erfc(t)
   // x * Phi(x) with Phi = 1 - e (x >= 0) or e (x < 0)  ==  max(x, 0) - |x| * e
