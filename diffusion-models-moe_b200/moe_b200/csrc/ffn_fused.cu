@@ -88,6 +88,13 @@ struct Barriers {
   uint64_t hs_empty[2];    // staging buffer stored by the sync warp
   uint64_t route_req;      // sync warp -> epilogue warps: a routing chunk is posted
   uint64_t route_done;     // 16 epilogue warps -> sync warp
+  // resident-A mode of phase 1 (Shape::a_resident): its own ring barriers (B operand only), the resident A block
+  // and the end of phase 1's tensor work
+  uint64_t full_b[kMaxStages];
+  uint64_t empty_b[kMaxStages];
+  uint64_t a_full;         // a row block's x panels have landed (leader CTA's copy counts both CTAs' bytes)
+  uint64_t a_empty;        // every MMA that reads the resident panels has completed
+  uint64_t p1_done;        // every phase-1 MMA has completed: shared memory may be re-carved for phase 3
   uint32_t tmem_base;
   int req_block, req_chunk;
   int last_cta;
@@ -99,6 +106,9 @@ struct Shape {
   // phase 1
   int nv, n_tiles1, ks1, nkb1, items1;
   int step_m1, step_n1;                         // a pair's next phase-1 tile: (mp, n) += (step_m1, step_n1), carry n -> mp
+  // resident-A mode (small d): a pair takes a contiguous run of tiles (same row block, consecutive column tiles), the
+  // row block's x panels stay in shared memory for the whole run and only W1 streams through the ring
+  int a_resident, a_res_bytes, stages1, slot1_bytes;
   int experts_per_tile, chunks_per_expert, span;
   // phase 3
   int bn, n_tiles3, ks3, nkb3, split3, kb_per_slice3, items3;
@@ -267,10 +277,25 @@ struct Item {
   int kb_begin, kb_end;    // k-block range
   int slice;
 };
-// phase-1 item `it` of pair `p` (P pairs): tile index p + it * P, row-block-major
+// phase-1 tiles of pair `p` (P pairs), row-block-major tile index: p, p + P, p + 2 P, ... (round-robin), or, in
+// resident-A mode, a contiguous run [begin, end) of a balanced partition (the first items1 % P pairs hold one more)
+__device__ __forceinline__ void range1(const Shape& g, int p, int P, int& begin, int& end, int& stride) {
+  if (g.a_resident) {
+    const int q = g.items1 / P, r = g.items1 - q * P;
+    begin = p * q + min(p, r);
+    end = begin + q + (p < r ? 1 : 0);
+    stride = 1;
+  } else {
+    begin = p;
+    end = g.items1;
+    stride = P;
+  }
+}
 __device__ __forceinline__ bool item1(const Shape& g, int it, int p, int P, int rm, Item& t) {
-  const int i = p + it * P;
-  if (i >= g.items1) return false;
+  int begin, end, stride;
+  range1(g, p, P, begin, end, stride);
+  const int i = begin + it * stride;
+  if (i >= end) return false;
   const int mp = i / g.n_tiles1;
   t.n = i - mp * g.n_tiles1;
   t.m_blk = 2 * mp + rm;
@@ -746,6 +771,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                  const __grid_constant__ CUtensorMap tmap_hs, const __grid_constant__ CUtensorMap tmap_hl,
                  const __grid_constant__ CUtensorMap tmap_w2, const __grid_constant__ CUtensorMap tmap_y,
                  const __grid_constant__ CUtensorMap tmap_hs_rem, const __grid_constant__ CUtensorMap tmap_y_rem,
+                 const __grid_constant__ CUtensorMap tmap_xres,
                  const Shape g, const Ptrs a) {
   extern __shared__ uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -781,6 +807,13 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     }
     tc::mbar_init(&bars->route_req, 1);
     tc::mbar_init(&bars->route_done, kEpiWarps);
+    for (int i = 0; i < kMaxStages; ++i) {
+      tc::mbar_init(&bars->full_b[i], 1);
+      tc::mbar_init(&bars->empty_b[i], 1);
+    }
+    tc::mbar_init(&bars->a_full, 1);
+    tc::mbar_init(&bars->a_empty, 1);
+    tc::mbar_init(&bars->p1_done, 1);
     tc::fence_mbar_init();
   }
   if (warp == 2) {
@@ -828,9 +861,24 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     int s = 0;
     uint32_t ph = 0;
     Item t;
-    const uint32_t full_leader0 = tc::mapa_u32(&bars->full[0], 0);
+    const bool ares = g.a_resident != 0;
     for (int phase = 0; phase < 2; ++phase) {
       const int ks = phase == 0 ? g.ks1 : g.ks3;
+      // resident-A mode: phase 1 has its own ring (B only, behind the resident panels) and barriers; phase 3 starts
+      // from a fresh ring over the whole area once every phase-1 MMA has completed
+      const bool res1 = ares && phase == 0;
+      uint64_t* const full_bar = res1 ? bars->full_b : bars->full;
+      uint64_t* const empty_bar = res1 ? bars->empty_b : bars->empty;
+      const int n_stages = res1 ? g.stages1 : g.stages;
+      const int slot_bytes = res1 ? g.slot1_bytes : g.slot_bytes;
+      uint8_t* const ring = res1 ? smem + g.a_res_bytes : smem;
+      const uint32_t full_leader0 = tc::mapa_u32(full_bar, 0);
+      if (ares && phase == 1) {
+        tc::mbar_wait(&bars->p1_done, 0u);
+        s = 0;
+        ph = 0;
+      }
+      int cur_mp = -1, a_runs = 0;
       for (int it = 0; phase == 0 ? item1(g, it, p, P, rm, t) : item3(g, it, p, P, rm, t); ++it) {
         if (phase == 1 && do_a) {
           // the block's H rows are complete and routed once every routing chunk of the block has been counted
@@ -847,32 +895,50 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           __syncwarp();
           fence_proxy_async_global();   // generic-proxy writes of other SMs (acquired above) -> this thread's TMA reads
         }
+        if (res1 && do_a) {
+          // one load per run of tiles on the same row block: all k-blocks of this CTA's 128 x rows
+          if ((t.m_blk >> 1) != cur_mp) {
+            cur_mp = t.m_blk >> 1;
+            if (a_runs > 0) tc::mbar_wait(&bars->a_empty, (a_runs - 1) & 1u);   // the previous block's MMAs are done
+            if (tc::elect_one()) {
+              if (rm == 0) tc::mbar_arrive_expect_tx(&bars->a_full, 2u * static_cast<uint32_t>(g.a_res_bytes));
+              tc::tma_load_3d_2sm(smem, &tmap_xres, tc::mapa_u32(&bars->a_full, 0), 0, t.m_blk * kBlockM, 0);
+#if MOE_TRACE
+              if (it == 0) TRACE(7);
+#endif
+            }
+            __syncwarp();
+            ++a_runs;
+          }
+          continue;
+        }
         for (int kb = t.kb_begin; kb < t.kb_end; kb += ks) {
-          tc::mbar_wait(&bars->empty[s], ph ^ 1u);
-          uint8_t* sa = smem + s * g.slot_bytes;
-          uint8_t* sb = sa + ks * kABytes;
+          tc::mbar_wait(&empty_bar[s], ph ^ 1u);
+          uint8_t* sa = ring + s * slot_bytes;
+          uint8_t* sb = res1 ? sa : sa + ks * kABytes;
           if (tc::elect_one()) {
             const uint32_t full_leader = full_leader0 + static_cast<uint32_t>(s) * 8u;
             if (phase == 0) {
               if (do_a) {
-                if (rm == 0) tc::mbar_arrive_expect_tx(&bars->full[s], 2u * bytes1);
+                if (rm == 0) tc::mbar_arrive_expect_tx(&full_bar[s], 2u * bytes1);
                 tc::tma_load_3d_2sm(sa, &tmap_x, full_leader, 0, t.m_blk * kBlockM, kb);
 #if MOE_TRACE
                 if (it == 0 && kb == 0) TRACE(7);
 #endif
               } else {
+                if (res1 && rm == 0) tc::mbar_arrive_expect_tx(&full_bar[s], 2u * static_cast<uint32_t>(g.slot1_bytes));
                 // CTA 0 of the pair stages the value rows, CTA 1 the gate rows of the tile's neurons
                 tc::tma_load_3d_2sm(sb, &tmap_w1, full_leader, 0, (rm == 0 ? 0 : g.h) + t.n * g.nv, kb);
               }
             } else if (do_a) {
-              if (rm == 0) tc::mbar_arrive_expect_tx(&bars->full[s], 2u * bytes3);
+              if (rm == 0) tc::mbar_arrive_expect_tx(&full_bar[s], 2u * bytes3);
               tc::tma_load_3d_2sm(sa, &tmap_hl, full_leader, 0, t.m_blk * kBlockM, kb);
             } else {
               tc::tma_load_3d_2sm(sb, &tmap_w2, full_leader, 0, t.n * g.bn + rm * (g.bn / 2), kb);
             }
           }
           __syncwarp();
-          if (++s == g.stages) {
+          if (++s == n_stages) {
             s = 0;
             ph ^= 1u;
           }
@@ -887,20 +953,53 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       int acc_it = 0;
       Item t;
       const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const bool ares = g.a_resident != 0;
       for (int phase = 0; phase < 2; ++phase) {
         const int ks = phase == 0 ? g.ks1 : g.ks3;
         const uint32_t idesc = tc::umma_idesc_bf16_f32(2 * kBlockM, static_cast<uint32_t>(phase == 0 ? 2 * g.nv : g.bn));
         const uint32_t b_sub_bytes = static_cast<uint32_t>((phase == 0 ? g.nv : g.bn / 2) * 128);
+        const bool res1 = ares && phase == 0;
+        uint64_t* const full_bar = res1 ? bars->full_b : bars->full;
+        uint64_t* const empty_bar = res1 ? bars->empty_b : bars->empty;
+        const int n_stages = res1 ? g.stages1 : g.stages;
+        const int slot_bytes = res1 ? g.slot1_bytes : g.slot_bytes;
+        const uint32_t ring = tc::smem_u32(smem) + (res1 ? static_cast<uint32_t>(g.a_res_bytes) : 0u);
+        const uint32_t a_res = tc::smem_u32(smem);
+        if (ares && phase == 1) {
+          s = 0;
+          ph = 0;
+        }
+        int cur_mp = -1, a_runs = 0;
         for (int it = 0; phase == 0 ? item1(g, it, p, P, rm, t) : item3(g, it, p, P, rm, t); ++it, ++acc_it) {
           const int as = acc_it & 1;
+          bool last_of_run = false;
+          if (res1) {
+            if ((t.m_blk >> 1) != cur_mp) {
+              cur_mp = t.m_blk >> 1;
+              tc::mbar_wait(&bars->a_full, a_runs & 1u);
+              ++a_runs;
+            }
+            Item nx;
+            last_of_run = !item1(g, it + 1, p, P, rm, nx) || (nx.m_blk >> 1) != cur_mp;
+          }
+#if MOE_TRACE
+          if (lane == 0 && acc_it == 4 && g.items1 > 5 * P) TRACE(50);
+#endif
           tc::mbar_wait(&bars->tmem_empty[as], ((acc_it >> 1) & 1u) ^ 1u);
           tc::fence_after_thread_sync();
+#if MOE_TRACE
+          if (lane == 0 && acc_it == 4 && g.items1 > 5 * P) TRACE(51);
+#endif
           const uint32_t d_tmem = tb + as * kAccStride;
           for (int kb = t.kb_begin; kb < t.kb_end; kb += ks) {
-            tc::mbar_wait(&bars->full[s], ph);
+            tc::mbar_wait(&full_bar[s], ph);
             tc::fence_after_thread_sync();
-            const uint32_t a_base = tc::smem_u32(smem + s * g.slot_bytes);
-            const uint32_t b_base = a_base + ks * kABytes;
+#if MOE_TRACE
+            if (lane == 0 && acc_it == 4 && g.items1 > 5 * P) TRACE(kb == t.kb_begin ? 52 : 53);
+#endif
+            const uint32_t slot = ring + s * slot_bytes;
+            const uint32_t a_base = res1 ? a_res + static_cast<uint32_t>(kb) * kABytes : slot;
+            const uint32_t b_base = res1 ? slot : slot + ks * kABytes;
             const int n_sub = min(ks, t.kb_end - kb);
             const bool leader_lane = tc::elect_one();
             if (leader_lane) {
@@ -917,22 +1016,25 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                   tc::umma_bf16_ss_2sm(d_tmem, da, db, idesc, (kb > t.kb_begin || sub != 0 || k != 0) ? 1u : 0u);
                 }
               }
-              tc::umma_commit_2sm_mc(&bars->empty[s], 0x3);   // frees the slot in both CTAs of the pair
+              tc::umma_commit_2sm_mc(&empty_bar[s], 0x3);   // frees the slot in both CTAs of the pair
             }
             __syncwarp();
-            if (++s == g.stages) {
+            if (++s == n_stages) {
               s = 0;
               ph ^= 1u;
             }
           }
           if (tc::elect_one()) {
             tc::umma_commit_2sm_mc(&bars->tmem_full[as], 0x3);   // accumulator complete -> both epilogues
+            if (last_of_run) tc::umma_commit_2sm_mc(&bars->a_empty, 0x3);   // the resident panels may be replaced
 #if MOE_TRACE
             if (acc_it < 13) TRACE(8 + 4 * acc_it);
 #endif
           }
           __syncwarp();
         }
+        if (res1 && tc::elect_one()) tc::umma_commit_2sm_mc(&bars->p1_done, 0x3);
+        __syncwarp();
       }
     }
   } else if (warp == 2) {
@@ -951,7 +1053,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         const int buf = st_it & 1;
         tc::mbar_wait(&bars->hs_full[buf], use_p1[buf] & 1u);
 #if MOE_TRACE
-        if (lane == 0 && it >= 2 && it < 6) TRACE(40 + 4 * (it - 2));
+        if (lane == 0 && it >= 2 && it < 4) TRACE(40 + 4 * (it - 2));
 #endif
         if (lane == 0) {
           const uint8_t* src = hstage + buf * g.hs_bytes;
@@ -982,7 +1084,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           tc::tma_store_wait_read<0>();
           tc::mbar_arrive(&bars->hs_empty[buf]);   // the epilogue warps may refill the buffer
 #if MOE_TRACE
-          if (it >= 2 && it < 6) TRACE(41 + 4 * (it - 2));
+          if (it >= 2 && it < 4) TRACE(41 + 4 * (it - 2));
 #endif
           Item nx;
           prev_blk = -1;
@@ -991,12 +1093,12 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           } else if (pending_blk >= 0) {
             tc::tma_store_wait<1>();        // every group but the one just committed is globally written
 #if MOE_TRACE
-            if (it >= 2 && it < 6) TRACE(42 + 4 * (it - 2));
+            if (it >= 2 && it < 4) TRACE(42 + 4 * (it - 2));
 #endif
             red_release_add(ws_rec + pending_blk * kBlockRecInts, 1);   // previous H tile + its scores, then the count
 #if MOE_TRACE
             if (st_it - 1 < 13) TRACE(8 + 4 * (st_it - 1) + 3);
-            if (it >= 2 && it < 6) TRACE(43 + 4 * (it - 2));
+            if (it >= 2 && it < 4) TRACE(43 + 4 * (it - 2));
 #endif
           }
         }
@@ -1089,7 +1191,9 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       const int cpe = g.chunks_per_expert;
       const int e_slot0 = (cpe > 0) ? cg * (cpg / g.es) : cg;
       const int act = g.act;
-      const int n_items1 = g.items1, n_tiles1 = g.n_tiles1, step_m1 = g.step_m1, step_n1 = g.step_n1;
+      const int n_tiles1 = g.n_tiles1, step_m1 = g.step_m1, step_n1 = g.step_n1;
+      int i1, n_items1, i_stride;       // this pair's tile indices: i1, i1 + i_stride, ... < n_items1
+      range1(g, p, P, i1, n_items1, i_stride);
       const long long score_row_stride = static_cast<long long>(kBlockM) * g.E;
       float* const score_row0 = a.scores + static_cast<long long>(rm * kBlockM + q_row) * g.E + e_slot0;
       const int experts_per_tile = g.experts_per_tile;
@@ -1099,7 +1203,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       const int nv = g.nv;
       const int rows_left0 = g.T - (rm * kBlockM + q_row);   // this row is inside the matrix iff rows_left0 > 256 mp
       // tile coordinates advance by a fixed step per iteration: no divisions in the loop
-      int i1 = p, mp1 = p / n_tiles1, n1 = p - (p / n_tiles1) * n_tiles1;
+      int mp1 = i1 / n_tiles1, n1 = i1 - (i1 / n_tiles1) * n_tiles1;
       // bias slices: the first tile's are staged up front, every later tile's are fetched into registers while
       // the previous tile is being processed (a staged load per tile exposed ~0.8 us of global latency each time)
       if (i1 < n_items1)
@@ -1109,7 +1213,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       for (; i1 < n_items1; ++it, ++acc_it) {
         const int mp_cur = mp1, n_cur = n1;
         // next tile of this pair
-        i1 += P;
+        i1 += i_stride;
         mp1 += step_m1;
         n1 += step_n1;
         if (n1 >= n_tiles1) {
@@ -1126,17 +1230,18 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           nb0 = __ldg(bv + lane);
           nb2 = __ldg(bv + g.h + lane);
         }
+        // this tile's addresses first: their dependent integer chains complete under the barrier waits below
+        const uint32_t taddr = taddr0 + as * kAccStride;
+        const uint32_t hbase = hbase0 + buf * hs_bytes;
+        float* spart_slot = spart + (buf * kBlockM + q_row) * kSpartPerRow + cg;
+        float* score_dst = score_row0 + 2 * mp_cur * score_row_stride + n_cur * experts_per_tile;
+        const bool score_ok = rows_left0 > 2 * kBlockM * mp_cur;
         if (ub > 0) tc::mbar_wait(&bars->hs_empty[buf], (ub - 1) & 1u);   // staging buffer drained
         tc::mbar_wait(&bars->tmem_full[as], (acc_it >> 1) & 1u);
         tc::fence_after_thread_sync();
 #if MOE_TRACE
         if (ew == 0 && lane == 0 && acc_it < 13) TRACE(8 + 4 * acc_it + 1);
 #endif
-        const uint32_t taddr = taddr0 + as * kAccStride;
-        const uint32_t hbase = hbase0 + buf * hs_bytes;
-        float* spart_slot = spart + (buf * kBlockM + q_row) * kSpartPerRow + cg;
-        float* score_dst = score_row0 + 2 * mp_cur * score_row_stride + n_cur * experts_per_tile;
-        const bool score_ok = rows_left0 > 2 * kBlockM * mp_cur;
         // (the alignment of the group's staging stores is warp-uniform: two instantiations, one uniform branch)
 #define MOE_GEGLU_GROUP(ACT_)                                                                                             \
   do {                                                                                                                    \
@@ -1541,6 +1646,21 @@ int moe_ffn_fused(const void* x, const void* w1p, const float* b1p, const void* 
   MOE_REQUIRE(g.stages >= 2, MOE_ERR_UNSUPPORTED_SHAPE, "moe_ffn_fused: tiles do not fit shared memory");
   g.ks1 = g.nkb1 >= 2 ? ks : 1;
   g.ks3 = ks;
+  // ---- resident-A mode of phase 1 (experimental, MOE_FUSED_ARES=1): a pair takes a contiguous run of column tiles
+  // and loads its 128 x d block of x once per run instead of once per tile, which cuts the L2 -> SM traffic of phase 1
+  // from 26 KB to 10 KB per k-block and CTA.  Measured slower (d = 320: 39.5 vs 37.2 us per layer call): the panels
+  // take 80 KB away from the W1 ring, and with less than two tiles of W1 in flight the ring's round trip
+  // (MMA complete -> slot free -> TMA -> landed) paces the tiles.  Off by default; kept for parity tests of the path.
+  g.a_resident = 0;
+  g.a_res_bytes = g.nkb1 * kABytes;
+  g.slot1_bytes = g.ks1 * nv * 128;
+  g.stages1 = (g.stages * g.slot_bytes - g.a_res_bytes) / g.slot1_bytes;
+  if (g.stages1 > kMaxStages) g.stages1 = kMaxStages;
+  if (const char* e = getenv("MOE_FUSED_ARES")) g.a_resident = (atoi(e) != 0 && g.stages1 >= 2 && g.items1 >= P && g.nkb1 <= 8) ? 1 : 0;
+  if (g.a_resident) {
+    g.step_m1 = 0;
+    g.step_n1 = 1;
+  }
   g.kb_per_slice3 = (g.nkb3 + g.split3 - 1) / g.split3;
   g.kb_per_slice3 = (g.kb_per_slice3 + g.ks3 - 1) / g.ks3 * g.ks3;
   while (g.split3 > 1 && (g.split3 - 1) * g.kb_per_slice3 >= g.nkb3) --g.split3;
@@ -1595,12 +1715,15 @@ int moe_ffn_fused(const void* x, const void* w1p, const float* b1p, const void* 
   if (getenv("MOE_DEBUG_PRINT"))
     fprintf(stderr,
             "[moe_ffn_fused] T=%d d=%d h=%d E=%d es=%d k=%d | nv=%d tiles1=%d ks1=%d | bn=%d tiles3=%d split=%d ks3=%d kb/slice=%d | "
-            "stages=%d slot=%d | route lanes=%d kpt=%d warps=%d chunks/block=%d | items %d + %d on %d pairs\n",
+            "stages=%d slot=%d resident-A=%d (ring %d x %d) | route lanes=%d kpt=%d warps=%d chunks/block=%d | items %d + %d on %d pairs\n",
             T, d, h, E, es, k, g.nv, g.n_tiles1, g.ks1, g.bn, g.n_tiles3, g.split3, g.ks3, g.kb_per_slice3, g.stages,
-            g.slot_bytes, g.lanes, g.kpt, g.route_warps, g.chunks_per_block, g.items1, g.items3, P);
+            g.slot_bytes, g.a_resident, g.stages1, g.slot1_bytes, g.lanes, g.kpt, g.route_warps, g.chunks_per_block, g.items1, g.items3, P);
 
-  CUtensorMap tx, tw1, ths, thl, tw2, ty, ths_rem, ty_rem;
+  CUtensorMap tx, tw1, ths, thl, tw2, ty, ths_rem, ty_rem, txres;
   int rc;
+  if ((rc = make_tmap_bf16_kblocks(&txres, x, static_cast<uint64_t>(T), static_cast<uint64_t>(d), kBlockM,
+                                   static_cast<uint32_t>(g.a_resident ? g.nkb1 : 1))))
+    return rc;
   if ((rc = make_tmap_bf16_kblocks(&tx, x, static_cast<uint64_t>(T), static_cast<uint64_t>(d), kBlockM, static_cast<uint32_t>(g.ks1)))) return rc;
   if ((rc = make_tmap_bf16_kblocks(&tw1, w1p, static_cast<uint64_t>(2) * h, static_cast<uint64_t>(d), static_cast<uint32_t>(nv),
                                    static_cast<uint32_t>(g.ks1))))
@@ -1662,7 +1785,7 @@ int moe_ffn_fused(const void* x, const void* w1p, const float* b1p, const void* 
   do {                                                                                              \
     rc = ensure_smem(reinterpret_cast<const void*>(ffn_fused_kernel<CHV>));                         \
     if (rc) return rc;                                                                              \
-    le = cudaLaunchKernelEx(&cfg, ffn_fused_kernel<CHV>, tx, tw1, ths, thl, tw2, ty, ths_rem, ty_rem, g, a); \
+    le = cudaLaunchKernelEx(&cfg, ffn_fused_kernel<CHV>, tx, tw1, ths, thl, tw2, ty, ths_rem, ty_rem, txres, g, a); \
   } while (0)
   switch (ch1) {
     case 32: MOE_LAUNCH_FUSED(32); break;

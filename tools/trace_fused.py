@@ -36,7 +36,7 @@ def show(name, tr, ms):
             break
         print(f"   item {it:2d}: mma-commit {col(b)} | epi-begin {col(b+1)} | epi-done {col(b+2)} | stored+signalled {col(b+3)}")
     print(f"   route: first begin {col(60)} | last end {col(61)} | K3 A-producer: ready-wait begin {col(62)} end {col(63)}")
-    for i in range(4):
+    for i in range(2):
         print(f"   sync warp, tile {i+2}: hs_full seen {col(40+4*i)} | stores read, buffer released {col(41+4*i)} | "
               f"previous tile's stores complete {col(42+4*i)} | previous tile published {col(43+4*i)}")
     print(f"   split-K epilogue (first phase-3 item): partials stored {col(48)} | counted {col(49)}")
@@ -45,6 +45,8 @@ def show(name, tr, ms):
         return f"{c.min():5.2f}/{c.median():5.2f}/{c.max():5.2f}" if len(c) else "-"
     print(f"   routing (last chunk of each CTA): whole item {d(60,61)} | select {d(56,57)} | labels/hist {d(57,58)} | "
           f"zero-writes {d(58,59)} | 59->end {d(59,61)}")
+    print(f"   MMA issuer, tile 4 (needs > 5 tiles per pair; us since tile 2 epi-done = its TMEM stage free): reaches tmem_empty wait {d(18,50)} | "
+          f"stage free seen {d(18,51)} | first k-block landed {d(18,52)} | last k-block landed {d(18,53)} | commit issued {d(18,24)} | epi-begin {d(18,25)}")
     print(f"   epi all done {col(4)} | teardown sync {col(5)} | exit {col(6)}")
 
 
