@@ -120,6 +120,18 @@ def test_fused_repeat_launches_share_workspace(lib):
     assert int(ws[:sync_bytes].view(torch.int32).abs().sum()) == 0
 
 
+@pytest.mark.parametrize("d,h,shape,es", [(320, 1280, (2, 2500), 20), (128, 640, (1, 9600), 20), (64, 256, (5, 4000), 16)])
+def test_fused_resident_a_mode_is_bit_identical(lib, monkeypatch, d, h, shape, es):
+    """MOE_FUSED_ARES=1 (experimental tile order of phase 1: contiguous runs of column tiles per CTA pair, the row
+    block's x panels resident in shared memory, ragged last row block): same bits as the default schedule."""
+    layer = O.synthetic_layer(d, h, shape, es, seed=11)
+    ref = fused_layer(layer, 0.3)
+    monkeypatch.setenv("MOE_FUSED_ARES", "1")
+    res = fused_layer(layer, 0.3, repeats=2)
+    for key in ("scores", "idx", "H", "y", "hist"):
+        assert torch.equal(ref[key], res[key]), key
+
+
 def test_fused_without_masking_is_the_dense_ffn(lib):
     """mask_h=False (the ExpertPredictivity contract, expert_activation.py:62: statistics only, unmasked output): the
     routing outputs are unchanged, H and Y are those of the dense FFN."""
