@@ -913,7 +913,13 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           continue;
         }
         for (int kb = t.kb_begin; kb < t.kb_end; kb += ks) {
+#if MOE_TRACE
+          if (do_a && lane == 0 && phase == 0 && it == 4 && kb == t.kb_begin && g.items1 > 5 * P) TRACE(54);
+#endif
           tc::mbar_wait(&empty_bar[s], ph ^ 1u);
+#if MOE_TRACE
+          if (do_a && lane == 0 && phase == 0 && it == 4 && kb + ks >= t.kb_end && g.items1 > 5 * P) TRACE(55);
+#endif
           uint8_t* sa = ring + s * slot_bytes;
           uint8_t* sb = res1 ? sa : sa + ks * kABytes;
           if (tc::elect_one()) {

@@ -47,6 +47,7 @@ def show(name, tr, ms):
           f"zero-writes {d(58,59)} | 59->end {d(59,61)}")
     print(f"   MMA issuer, tile 4 (needs > 5 tiles per pair; us since tile 2 epi-done = its TMEM stage free): reaches tmem_empty wait {d(18,50)} | "
           f"stage free seen {d(18,51)} | first k-block landed {d(18,52)} | last k-block landed {d(18,53)} | commit issued {d(18,24)} | epi-begin {d(18,25)}")
+    print(f"   A producer, tile 4 (same origin): reaches first slot wait {d(18,54)} | last slot free seen {d(18,55)} ; tile 3 commit issued {d(18,20)}")
     print(f"   epi all done {col(4)} | teardown sync {col(5)} | exit {col(6)}")
 
 
