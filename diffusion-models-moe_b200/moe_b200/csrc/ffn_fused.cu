@@ -109,6 +109,11 @@ struct Shape {
   // resident-A mode (small d): a pair takes a contiguous run of tiles (same row block, consecutive column tiles), the
   // row block's x panels stay in shared memory for the whole run and only W1 streams through the ring
   int a_resident, a_res_bytes, stages1, slot1_bytes;
+  // phase 1 on its own ring (barriers full_b / empty_b, `stages1` slots of `slot1_bytes` from byte `ring1_off`): set by
+  // resident-A mode and by direct-H mode, where the epilogue stores H straight to global memory and the staging
+  // buffers' space becomes a fourth ring slot for the phase whose main loop is bound by k-blocks in flight
+  int sep_ring1, ring1_off, direct_h;
+  int tail_off, spart_bytes;                    // small per-warp arrays + barriers start at tail_off
   int experts_per_tile, chunks_per_expert, span;
   // phase 3
   int bn, n_tiles3, ks3, nkb3, split3, kb_per_slice3, items3;
@@ -703,9 +708,25 @@ __device__ __forceinline__ void st_global_if(float* p, float v, bool pred) {
 //   cpe                chunks per expert when whole experts lie inside a column group, else 0
 //   score_dst          global slot of the group's first expert score for this row (stored only if score_ok)
 //   spart_slot         shared-memory slot of this group's partial sum (experts that span column groups)
-template <int CH, int ACT, bool kAligned>
+// direct-H mode: kWords words (2 columns each) of one row straight to global memory; `aligned` = dst is 16-byte aligned
+template <int kWords, bool aligned>
+__device__ __forceinline__ void global_store_row(__nv_bfloat16* dst, const uint32_t* w) {
+  uint32_t* d = reinterpret_cast<uint32_t*>(dst);
+  if constexpr (aligned) {
+#pragma unroll
+    for (int i = 0; i + 4 <= kWords; i += 4) *reinterpret_cast<uint4*>(d + i) = make_uint4(w[i], w[i + 1], w[i + 2], w[i + 3]);
+    if constexpr (kWords % 4 != 0) *reinterpret_cast<uint2*>(d + kWords - 2) = make_uint2(w[kWords - 2], w[kWords - 1]);
+  } else {
+    *reinterpret_cast<uint2*>(d) = make_uint2(w[0], w[1]);
+#pragma unroll
+    for (int i = 2; i + 4 <= kWords; i += 4) *reinterpret_cast<uint4*>(d + i) = make_uint4(w[i], w[i + 1], w[i + 2], w[i + 3]);
+    if constexpr (kWords % 4 == 0) *reinterpret_cast<uint2*>(d + kWords - 2) = make_uint2(w[kWords - 2], w[kWords - 1]);
+  }
+}
+
+template <int CH, int ACT, bool kAligned, bool kDirect>
 __device__ __forceinline__ void geglu_group(uint32_t taddr_v, uint32_t taddr_g, const float* sbias, uint32_t hbase,
-                                            const uint32_t (&piece_off)[8], float* spart_slot,
+                                            const uint32_t (&piece_off)[8], __nv_bfloat16* hrow, float* spart_slot,
                                             float* score_dst, bool score_ok, int cpg, int cpe) {
   uint64_t score2 = pk2(0.f, 0.f);
   int chunk_in_expert = 0;
@@ -747,7 +768,11 @@ __device__ __forceinline__ void geglu_group(uint32_t taddr_v, uint32_t taddr_g, 
       hw[i / 2] = pack_bf16x2(h0, h1);
       hw[i / 2 + 1] = pack_bf16x2(h2, h3);
     }
-    stage_store_pre<CH / 2, kAligned>(hbase, &piece_off[(ci * CH) / 4], hw);
+    if constexpr (kDirect) {
+      if (score_ok) global_store_row<CH / 2, kAligned>(hrow + c, hw);   // (score_ok: the row is inside the matrix)
+    } else {
+      stage_store_pre<CH / 2, kAligned>(hbase, &piece_off[(ci * CH) / 4], hw);
+    }
     if (cpe > 0 && ++chunk_in_expert == cpe) {
       float s0, s1;
       unpk2(score2, s0, s1);
@@ -778,9 +803,9 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   if (threadIdx.x == 0) TRACE(0);
   uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* hstage = smem + g.stages * g.slot_bytes;
-  float* sbias_all = reinterpret_cast<float*>(hstage + 2 * g.hs_bytes);
-  float* spart = sbias_all + kEpiWarps * (kBiasBytesPerWarp / 4);             // [2][128][kSpartPerRow]
-  uint32_t* s_words_all = reinterpret_cast<uint32_t*>(spart + 2 * kBlockM * kSpartPerRow);   // [16 warps][16]: tokens per warp x words
+  float* sbias_all = reinterpret_cast<float*>(smem + g.tail_off);
+  float* spart = sbias_all + kEpiWarps * (kBiasBytesPerWarp / 4);             // [2][128][kSpartPerRow], or empty
+  uint32_t* s_words_all = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(spart) + g.spart_bytes);   // [16 warps][16]: tokens per warp x words
   unsigned int* s_hist = s_words_all + kEpiWarps * 16;                        // [kMaxExperts]
   Barriers* bars = reinterpret_cast<Barriers*>(s_hist + kMaxExperts);
 
@@ -867,13 +892,14 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       // resident-A mode: phase 1 has its own ring (B only, behind the resident panels) and barriers; phase 3 starts
       // from a fresh ring over the whole area once every phase-1 MMA has completed
       const bool res1 = ares && phase == 0;
-      uint64_t* const full_bar = res1 ? bars->full_b : bars->full;
-      uint64_t* const empty_bar = res1 ? bars->empty_b : bars->empty;
-      const int n_stages = res1 ? g.stages1 : g.stages;
-      const int slot_bytes = res1 ? g.slot1_bytes : g.slot_bytes;
-      uint8_t* const ring = res1 ? smem + g.a_res_bytes : smem;
+      const bool sep1 = g.sep_ring1 != 0 && phase == 0;
+      uint64_t* const full_bar = sep1 ? bars->full_b : bars->full;
+      uint64_t* const empty_bar = sep1 ? bars->empty_b : bars->empty;
+      const int n_stages = sep1 ? g.stages1 : g.stages;
+      const int slot_bytes = sep1 ? g.slot1_bytes : g.slot_bytes;
+      uint8_t* const ring = sep1 ? smem + g.ring1_off : smem;
       const uint32_t full_leader0 = tc::mapa_u32(full_bar, 0);
-      if (ares && phase == 1) {
+      if (g.sep_ring1 != 0 && phase == 1) {
         tc::mbar_wait(&bars->p1_done, 0u);
         s = 0;
         ph = 0;
@@ -965,13 +991,14 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         const uint32_t idesc = tc::umma_idesc_bf16_f32(2 * kBlockM, static_cast<uint32_t>(phase == 0 ? 2 * g.nv : g.bn));
         const uint32_t b_sub_bytes = static_cast<uint32_t>((phase == 0 ? g.nv : g.bn / 2) * 128);
         const bool res1 = ares && phase == 0;
-        uint64_t* const full_bar = res1 ? bars->full_b : bars->full;
-        uint64_t* const empty_bar = res1 ? bars->empty_b : bars->empty;
-        const int n_stages = res1 ? g.stages1 : g.stages;
-        const int slot_bytes = res1 ? g.slot1_bytes : g.slot_bytes;
-        const uint32_t ring = tc::smem_u32(smem) + (res1 ? static_cast<uint32_t>(g.a_res_bytes) : 0u);
+        const bool sep1 = g.sep_ring1 != 0 && phase == 0;
+        uint64_t* const full_bar = sep1 ? bars->full_b : bars->full;
+        uint64_t* const empty_bar = sep1 ? bars->empty_b : bars->empty;
+        const int n_stages = sep1 ? g.stages1 : g.stages;
+        const int slot_bytes = sep1 ? g.slot1_bytes : g.slot_bytes;
+        const uint32_t ring = tc::smem_u32(smem) + (sep1 ? static_cast<uint32_t>(g.ring1_off) : 0u);
         const uint32_t a_res = tc::smem_u32(smem);
-        if (ares && phase == 1) {
+        if (g.sep_ring1 != 0 && phase == 1) {
           s = 0;
           ph = 0;
         }
@@ -1039,7 +1066,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           }
           __syncwarp();
         }
-        if (res1 && tc::elect_one()) tc::umma_commit_2sm_mc(&bars->p1_done, 0x3);
+        if (sep1 && tc::elect_one()) tc::umma_commit_2sm_mc(&bars->p1_done, 0x3);
         __syncwarp();
       }
     }
@@ -1061,7 +1088,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 #if MOE_TRACE
         if (lane == 0 && it >= 2 && it < 4) TRACE(40 + 4 * (it - 2));
 #endif
-        if (lane == 0) {
+        if (lane == 0 && !g.direct_h) {   // (direct-H mode: the epilogue threads have already stored the tile)
           const uint8_t* src = hstage + buf * g.hs_bytes;
           const int n_full = g.nv >> 6;
           for (int pn = 0; pn < n_full; ++pn)
@@ -1207,6 +1234,9 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       const uint32_t hbase0 = tc::smem_u32(hstage);
       const uint32_t hs_bytes = g.hs_bytes;
       const int nv = g.nv;
+      const bool direct_h = g.direct_h != 0;
+      const long long h_row_stride = static_cast<long long>(kBlockM) * g.h;
+      __nv_bfloat16* const h_row0 = a.H + static_cast<long long>(rm * kBlockM + q_row) * g.h + col0;
       const int rows_left0 = g.T - (rm * kBlockM + q_row);   // this row is inside the matrix iff rows_left0 > 256 mp
       // tile coordinates advance by a fixed step per iteration: no divisions in the loop
       int mp1 = i1 / n_tiles1, n1 = i1 - (i1 / n_tiles1) * n_tiles1;
@@ -1242,6 +1272,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         float* spart_slot = spart + (buf * kBlockM + q_row) * kSpartPerRow + cg;
         float* score_dst = score_row0 + 2 * mp_cur * score_row_stride + n_cur * experts_per_tile;
         const bool score_ok = rows_left0 > 2 * kBlockM * mp_cur;
+        __nv_bfloat16* hrow = h_row0 + 2 * mp_cur * h_row_stride + n_cur * nv;   // direct-H mode only
         if (ub > 0) tc::mbar_wait(&bars->hs_empty[buf], (ub - 1) & 1u);   // staging buffer drained
         tc::mbar_wait(&bars->tmem_full[as], (acc_it >> 1) & 1u);
         tc::fence_after_thread_sync();
@@ -1249,18 +1280,27 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         if (ew == 0 && lane == 0 && acc_it < 13) TRACE(8 + 4 * acc_it + 1);
 #endif
         // (the alignment of the group's staging stores is warp-uniform: two instantiations, one uniform branch)
-#define MOE_GEGLU_GROUP(ACT_)                                                                                             \
-  do {                                                                                                                    \
-    if (aligned)                                                                                                          \
-      geglu_group<CH, ACT_, true>(taddr, taddr + nv, sbias, hbase, piece_off, spart_slot, score_dst, score_ok, cpg, cpe); \
-    else                                                                                                                  \
-      geglu_group<CH, ACT_, false>(taddr, taddr + nv, sbias, hbase, piece_off, spart_slot, score_dst, score_ok, cpg, cpe); \
+#define MOE_GEGLU_CALL(ACT_, AL_, DIR_) \
+  geglu_group<CH, ACT_, AL_, DIR_>(taddr, taddr + nv, sbias, hbase, piece_off, hrow, spart_slot, score_dst, score_ok, cpg, cpe)
+#define MOE_GEGLU_GROUP(ACT_)              \
+  do {                                     \
+    if (direct_h) {                        \
+      if (aligned)                         \
+        MOE_GEGLU_CALL(ACT_, true, true);  \
+      else                                 \
+        MOE_GEGLU_CALL(ACT_, false, true); \
+    } else if (aligned) {                  \
+      MOE_GEGLU_CALL(ACT_, true, false);   \
+    } else {                               \
+      MOE_GEGLU_CALL(ACT_, false, false);  \
+    }                                      \
   } while (0)
         if (act == MOE_ACT_GELU) MOE_GEGLU_GROUP(MOE_ACT_GELU);
 #if MOE_TRACE
         else if (act == 2) MOE_GEGLU_GROUP(2);
 #endif
         else MOE_GEGLU_GROUP(MOE_ACT_RELU);
+#undef MOE_GEGLU_CALL
 #undef MOE_GEGLU_GROUP
         // accumulator stage drained -> the leader's MMA thread may overwrite it
         tc::fence_before_thread_sync();
@@ -1271,7 +1311,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           sbias[64 + lane] = nb2;
         }
         // H tile: generic-proxy smem writes -> async proxy; the sync warp stores it and publishes the tile
-        tc::fence_proxy_async_smem();
+        if (!direct_h) tc::fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&bars->hs_full[buf]);
 #if MOE_TRACE
@@ -1635,9 +1675,10 @@ int moe_ffn_fused(const void* x, const void* w1p, const float* b1p, const void* 
 
   // ---- pipeline: k-blocks per stage (2 if at least 3 stages fit), ring slot = the larger of the two phases
   g.hs_bytes = kBlockM * nv * 2;
-  const int fixed = 1024 + 2 * g.hs_bytes + kEpiWarps * kBiasBytesPerWarp + 2 * kBlockM * kSpartPerRow * 4 +
-                    kEpiWarps * 16 * 4 + kMaxExperts * 4 +
+  g.spart_bytes = (g.chunks_per_expert == 0) ? 2 * kBlockM * kSpartPerRow * 4 : 0;   // only experts that span column groups
+  const int small = kEpiWarps * kBiasBytesPerWarp + g.spart_bytes + kEpiWarps * 16 * 4 + kMaxExperts * 4 +
                     static_cast<int>(sizeof(Barriers)) + 64;
+  const int fixed = 1024 + 2 * g.hs_bytes + small;
   int ks = 2;
   if (const char* e = getenv("MOE_FUSED_KS")) ks = atoi(e) == 1 ? 1 : 2;
   for (; ks >= 1; --ks) {
@@ -1649,6 +1690,10 @@ int moe_ffn_fused(const void* x, const void* w1p, const float* b1p, const void* 
       break;
     }
   }
+  if (const char* e = getenv("MOE_FUSED_STAGES")) {   // experiments only: a shallower ring
+    const int v = atoi(e);
+    if (v >= 2 && v < g.stages) g.stages = v;
+  }
   MOE_REQUIRE(g.stages >= 2, MOE_ERR_UNSUPPORTED_SHAPE, "moe_ffn_fused: tiles do not fit shared memory");
   g.ks1 = g.nkb1 >= 2 ? ks : 1;
   g.ks3 = ks;
@@ -1657,6 +1702,10 @@ int moe_ffn_fused(const void* x, const void* w1p, const float* b1p, const void* 
   // from 26 KB to 10 KB per k-block and CTA.  Measured slower (d = 320: 39.5 vs 37.2 us per layer call): the panels
   // take 80 KB away from the W1 ring, and with less than two tiles of W1 in flight the ring's round trip
   // (MMA complete -> slot free -> TMA -> landed) paces the tiles.  Off by default; kept for parity tests of the path.
+  g.tail_off = g.stages * g.slot_bytes + 2 * g.hs_bytes;
+  g.sep_ring1 = 0;
+  g.ring1_off = 0;
+  g.direct_h = 0;
   g.a_resident = 0;
   g.a_res_bytes = g.nkb1 * kABytes;
   g.slot1_bytes = g.ks1 * nv * 128;
@@ -1666,6 +1715,27 @@ int moe_ffn_fused(const void* x, const void* w1p, const float* b1p, const void* 
   if (g.a_resident) {
     g.step_m1 = 0;
     g.step_n1 = 1;
+    g.sep_ring1 = 1;
+    g.ring1_off = g.a_res_bytes;
+  }
+  // ---- direct-H mode of phase 1 (experimental, MOE_FUSED_DIRECT=1): the epilogue threads store their H rows straight
+  // to global memory and the 2 x 20 KB of staging become a fourth ring slot for phase 1 (phase 3 keeps the staging for
+  // its Y tiles).  Measured: d = 1280 / 512 tokens 39.7 vs 40.2 us, d = 640 35.6 vs 33.8 us -- a deeper ring does not
+  // buy what a shallower one costs (2 slots: +6 us), so the L2 -> SM delivery rate, not the ring depth, is the limit,
+  // and the uncoalesced row stores lengthen the epilogue.  Off by default; kept for parity tests of the path.
+  if (!g.a_resident) {
+    int stages_d = (kSmemLimit - 1024 - small) / g.slot_bytes;
+    if (stages_d > kMaxStages) stages_d = kMaxStages;
+    bool on = false;
+    if (const char* e = getenv("MOE_FUSED_DIRECT")) on = atoi(e) != 0 && stages_d >= g.stages;
+    if (on) {
+      g.direct_h = 1;
+      g.sep_ring1 = 1;
+      g.ring1_off = 0;
+      g.stages1 = stages_d;
+      g.slot1_bytes = g.slot_bytes;
+      if (g.stages1 * g.slot1_bytes > g.tail_off) g.tail_off = g.stages1 * g.slot1_bytes;
+    }
   }
   g.kb_per_slice3 = (g.nkb3 + g.split3 - 1) / g.split3;
   g.kb_per_slice3 = (g.kb_per_slice3 + g.ks3 - 1) / g.ks3 * g.ks3;
@@ -1721,9 +1791,9 @@ int moe_ffn_fused(const void* x, const void* w1p, const float* b1p, const void* 
   if (getenv("MOE_DEBUG_PRINT"))
     fprintf(stderr,
             "[moe_ffn_fused] T=%d d=%d h=%d E=%d es=%d k=%d | nv=%d tiles1=%d ks1=%d | bn=%d tiles3=%d split=%d ks3=%d kb/slice=%d | "
-            "stages=%d slot=%d resident-A=%d (ring %d x %d) | route lanes=%d kpt=%d warps=%d chunks/block=%d | items %d + %d on %d pairs\n",
+            "stages=%d slot=%d resident-A=%d direct-H=%d (ring1 %d x %d) | route lanes=%d kpt=%d warps=%d chunks/block=%d | items %d + %d on %d pairs\n",
             T, d, h, E, es, k, g.nv, g.n_tiles1, g.ks1, g.bn, g.n_tiles3, g.split3, g.ks3, g.kb_per_slice3, g.stages,
-            g.slot_bytes, g.a_resident, g.stages1, g.slot1_bytes, g.lanes, g.kpt, g.route_warps, g.chunks_per_block, g.items1, g.items3, P);
+            g.slot_bytes, g.a_resident, g.direct_h, g.stages1, g.slot1_bytes, g.lanes, g.kpt, g.route_warps, g.chunks_per_block, g.items1, g.items3, P);
 
   CUtensorMap tx, tw1, ths, thl, tw2, ty, ths_rem, ty_rem, txres;
   int rc;
@@ -1769,7 +1839,7 @@ int moe_ffn_fused(const void* x, const void* w1p, const float* b1p, const void* 
   a.split_counters = reinterpret_cast<int*>(static_cast<uint8_t*>(workspace) + kSyncBytes);
   a.split_partial = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + kSyncBytes + kSplitCounterBytes);
 
-  const size_t smem = static_cast<size_t>(fixed) + static_cast<size_t>(g.stages) * g.slot_bytes;
+  const size_t smem = 1024u + static_cast<size_t>(g.tail_off) + static_cast<size_t>(small);
   MOE_REQUIRE(smem <= static_cast<size_t>(kSmemLimit), MOE_ERR_UNSUPPORTED_SHAPE, "moe_ffn_fused: smem %zu", smem);
 
   cudaLaunchConfig_t cfg = {};

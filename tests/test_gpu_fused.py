@@ -120,13 +120,17 @@ def test_fused_repeat_launches_share_workspace(lib):
     assert int(ws[:sync_bytes].view(torch.int32).abs().sum()) == 0
 
 
-@pytest.mark.parametrize("d,h,shape,es", [(320, 1280, (2, 2500), 20), (128, 640, (1, 9600), 20), (64, 256, (5, 4000), 16)])
-def test_fused_resident_a_mode_is_bit_identical(lib, monkeypatch, d, h, shape, es):
-    """MOE_FUSED_ARES=1 (experimental tile order of phase 1: contiguous runs of column tiles per CTA pair, the row
-    block's x panels resident in shared memory, ragged last row block): same bits as the default schedule."""
+@pytest.mark.parametrize("env", ["MOE_FUSED_ARES", "MOE_FUSED_DIRECT"])
+@pytest.mark.parametrize("d,h,shape,es", [(320, 1280, (2, 2500), 20), (128, 640, (1, 9600), 20), (64, 256, (5, 4000), 16),
+                                          (640, 2560, (1, 700), 20)])
+def test_fused_experimental_schedules_are_bit_identical(lib, monkeypatch, env, d, h, shape, es):
+    """The two experimental phase-1 schedules (off by default) give the same bits as the default:
+    MOE_FUSED_ARES=1 -- contiguous runs of column tiles per CTA pair with the row block's x panels resident in shared
+    memory; MOE_FUSED_DIRECT=1 -- H rows stored straight from the epilogue threads, the staging space used as ring slots.
+    Both put phase 1 on its own ring and re-carve shared memory for phase 3; ragged last row block included."""
     layer = O.synthetic_layer(d, h, shape, es, seed=11)
     ref = fused_layer(layer, 0.3)
-    monkeypatch.setenv("MOE_FUSED_ARES", "1")
+    monkeypatch.setenv(env, "1")
     res = fused_layer(layer, 0.3, repeats=2)
     for key in ("scores", "idx", "H", "y", "hist"):
         assert torch.equal(ref[key], res[key]), key
