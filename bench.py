@@ -435,7 +435,7 @@ def gpu_arm(args):
                         peak=peak_tf, unit="TFLOP/s", frac=round(tf / peak_tf, 4),
                         # ncu --set full, dram__bytes_read + write of one launch (profiles/r01_ncu_full_fused_layer_d320.csv;
                         # d = 320, 8192 tokens: x 5.2 MB + weights 2.5 MB in, Y still in L2; H never leaves L2)
-                        traffic=8.61e6, traffic_launch="ffn_fused_kernel d=320 T=8192", peak_source=peak_src,
+                        traffic=7.93e6, traffic_launch="ffn_fused_kernel d=320 T=8192", peak_source=peak_src,
                         algorithmic="6*d*h FLOP per token (4dh up-projection + 2dh dense-equivalent down-projection), "
                                     "summed over the step's 16 launches / the step time (CUDA events; the timed region "
                                     "holds nothing but these launches)")
