@@ -156,6 +156,30 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------- GPU arm
+def bind_to_gpu_numa_node(index):
+    """Pin this process to the CPUs local to GPU `index` (sysfs local_cpulist of its PCI function), so that the pinned
+    host arenas of the e2e leg are allocated on the NUMA node the GPU hangs off.  Best effort: returns a description."""
+    try:
+        pr = torch.cuda.get_device_properties(index)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bdf}"
+        node = open(f"{base}/numa_node").read().strip()
+        cpus = set()
+        for part in open(f"{base}/local_cpulist").read().strip().split(","):
+            if not part:
+                continue
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if use and use != allowed:
+            os.sched_setaffinity(0, use)
+            return f"gpu {bdf} node {node}: bound to {len(use)} of {len(allowed)} cpus"
+        return f"gpu {bdf} node {node}: {len(allowed)} cpus allowed, no narrowing"
+    except Exception as e:      # noqa: BLE001 -- sysfs layout differs between hosts; the bench runs unbound then
+        return f"unbound ({type(e).__name__})"
+
+
 def gpu_arm(args):
     import moe_b200 as M
     from moe_b200.packing import ExpertLayout, pack_ffn
@@ -165,6 +189,7 @@ def gpu_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local)     # before any pinned allocation: host pages land next to the GPU's PCIe root
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -467,7 +492,7 @@ def gpu_arm(args):
                 unet_steps_per_s=world * 1e3 / ms_step,
                 e2e=dict(value=world * tokens_per_step / (ms_e2e * 1e-3), unit="tokens/s", h2d_bytes_per_step=h2d,
                          d2h_bytes_per_step=d2h, ms_per_step=ms_e2e, cuda_graph=e2e_graph is not None,
-                         copies_per_step=2 * len(groups) + 1, pipelined_steps=True,
+                         copies_per_step=2 * len(groups) + 1, pipelined_steps=True, host_binding=numa,
                          output_abs_sum_layer0=y_check, outputs_equal_resident_run=e2e_same),
                 gpu_launches=launches_per_step * args.steps, clocks=clocks, roofline=roofline,
                 histogram_counts_exact=counts_ok)
