@@ -33,6 +33,13 @@
 //   warp 3      B-tile TMA producer (W1 / W2 slices; weights have no dependencies, so it runs ahead)
 //   warps 4-19  epilogue: TMEM -> registers -> bias / exact GELU / product (packed f32x2 math) -> bf16 ->
 //               smem staging; expert scores; routing chunks on request; phase-3 maskers; split-K reduction
+//
+// Two experimental schedules of phase 1 are kept behind environment switches (both measured neutral to slower, both
+// bit-identical to the default and parity-tested): MOE_FUSED_ARES=1 keeps a row block's x panels
+// resident in shared memory and streams only W1 through the ring (contiguous runs of column tiles per CTA pair);
+// MOE_FUSED_DIRECT=1 stores H straight from the epilogue threads and turns the staging buffers into a fourth ring
+// slot.  Both run phase 1 on its own ring (barriers full_b / empty_b) and re-carve shared memory for phase 3 once
+// every phase-1 MMA has completed (p1_done).
 #include "common.cuh"
 #include "tcgen05.cuh"
 
@@ -79,7 +86,7 @@ __device__ unsigned long long g_trace[256 * 64];
   } while (0)
 #endif
 
-struct Barriers {
+struct Barriers {   // the mbarriers first, in this order: the kernel initialises them by index
   uint64_t full[kMaxStages];
   uint64_t empty[kMaxStages];
   uint64_t tmem_full[2];
@@ -819,26 +826,20 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     tc::prefetch_tensormap(&tmap_hl);
     tc::prefetch_tensormap(&tmap_w2);
   }
-  if (warp == 1 && lane == 0) {
-    for (int i = 0; i < g.stages; ++i) {
-      tc::mbar_init(&bars->full[i], 1);
-      tc::mbar_init(&bars->empty[i], 1);
+  if (warp == 1) {
+    // one barrier per lane (the struct starts with its mbarriers, in declaration order); the separate phase-1 ring
+    // and its hand-over barriers only when a schedule uses them
+    constexpr int kCore = 2 * kMaxStages + 10;                 // full, empty, tmem_*, hs_*, route_*
+    constexpr int kAll = kCore + 2 * kMaxStages + 3;           // + full_b, empty_b, a_full, a_empty, p1_done
+    uint64_t* const all = reinterpret_cast<uint64_t*>(bars);
+    const int n_init = g.sep_ring1 ? kAll : kCore;
+    for (int i = lane; i < n_init; i += 32) {
+      uint32_t count = 1;
+      if (i == 2 * kMaxStages + 2 || i == 2 * kMaxStages + 3) count = 2 * kEpiWarps;   // tmem_empty: both CTAs' epilogues
+      if (i == 2 * kMaxStages + 4 || i == 2 * kMaxStages + 5) count = kEpiWarps;       // hs_full
+      if (i == 2 * kMaxStages + 9) count = kEpiWarps;                                  // route_done
+      tc::mbar_init(all + i, count);
     }
-    for (int i = 0; i < 2; ++i) {
-      tc::mbar_init(&bars->tmem_full[i], 1);
-      tc::mbar_init(&bars->tmem_empty[i], 2 * kEpiWarps);   // both CTAs' epilogues release the leader's MMA thread
-      tc::mbar_init(&bars->hs_full[i], kEpiWarps);
-      tc::mbar_init(&bars->hs_empty[i], 1);
-    }
-    tc::mbar_init(&bars->route_req, 1);
-    tc::mbar_init(&bars->route_done, kEpiWarps);
-    for (int i = 0; i < kMaxStages; ++i) {
-      tc::mbar_init(&bars->full_b[i], 1);
-      tc::mbar_init(&bars->empty_b[i], 1);
-    }
-    tc::mbar_init(&bars->a_full, 1);
-    tc::mbar_init(&bars->a_empty, 1);
-    tc::mbar_init(&bars->p1_done, 1);
     tc::fence_mbar_init();
   }
   if (warp == 2) {
