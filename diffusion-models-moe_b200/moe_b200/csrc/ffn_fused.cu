@@ -1553,10 +1553,11 @@ int moe_ffn_fused(const void* x, const void* w1p, const float* b1p, const void* 
                   int mask_h, void* workspace, size_t workspace_bytes, void* stream) {
   using namespace moe;
   using namespace moe::fused;
-  MOE_REQUIRE(x && w1p && w2p && H && scores && Y && workspace, MOE_ERR_INVALID_ARGUMENT,
-              "moe_ffn_fused: NULL x / w1p / w2p / H / scores / Y / workspace");
   MOE_REQUIRE(T >= 0 && d >= 8 && h >= 8 && E >= 1 && es >= 1 && k >= 0 && k <= E, MOE_ERR_INVALID_ARGUMENT,
               "moe_ffn_fused: bad sizes T=%d d=%d h=%d E=%d es=%d k=%d", T, d, h, E, es, k);
+  if (T == 0) return MOE_OK;   // an empty shard: nothing to compute, and empty tensors have no storage to point at
+  MOE_REQUIRE(x && w1p && w2p && H && scores && Y && workspace, MOE_ERR_INVALID_ARGUMENT,
+              "moe_ffn_fused: NULL x / w1p / w2p / H / scores / Y / workspace");
   MOE_REQUIRE(static_cast<long long>(E) * es == h, MOE_ERR_INVALID_ARGUMENT, "moe_ffn_fused: E*es=%d*%d != h=%d", E, es, h);
   MOE_REQUIRE(act == MOE_ACT_GELU || act == MOE_ACT_RELU || (MOE_TRACE && act == 2), MOE_ERR_INVALID_ARGUMENT,
               "moe_ffn_fused: act=%d", act);

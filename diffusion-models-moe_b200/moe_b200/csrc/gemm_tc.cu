@@ -935,9 +935,10 @@ int moe_geglu_up(const void* x, const void* w1p, const float* b1p, const uint8_t
                  float override_value, void* H, float* scores, void* gate_out, int T, int d, int h, int E,
                  int es, int act, void* stream) {
   using namespace moe;
-  MOE_REQUIRE(x && w1p && H, MOE_ERR_INVALID_ARGUMENT, "moe_geglu_up: NULL x / w1p / H");
   MOE_REQUIRE(T >= 0 && d >= 8 && h >= 8 && E >= 1 && es >= 1, MOE_ERR_INVALID_ARGUMENT,
               "moe_geglu_up: bad sizes T=%d d=%d h=%d E=%d es=%d", T, d, h, E, es);
+  if (T == 0) return MOE_OK;   // empty tensors have no storage to point at
+  MOE_REQUIRE(x && w1p && H, MOE_ERR_INVALID_ARGUMENT, "moe_geglu_up: NULL x / w1p / H");
   MOE_REQUIRE(static_cast<long long>(E) * es == h, MOE_ERR_INVALID_ARGUMENT, "moe_geglu_up: E*es=%d*%d != h=%d", E, es, h);
   MOE_REQUIRE(d % 8 == 0 && h % 8 == 0, MOE_ERR_UNSUPPORTED_SHAPE, "moe_geglu_up: d=%d and h=%d must be multiples of 8", d, h);
   MOE_REQUIRE(act == MOE_ACT_GELU || act == MOE_ACT_RELU, MOE_ERR_INVALID_ARGUMENT, "moe_geglu_up: act=%d", act);
@@ -1057,8 +1058,9 @@ size_t moe_down_proj_workspace_bytes(int T, int h, int d) {
 int moe_down_proj(const void* H, const void* w2p, const float* b2, void* Y, int T, int h, int d, void* workspace,
                   size_t workspace_bytes, void* stream) {
   using namespace moe;
-  MOE_REQUIRE(H && w2p && Y, MOE_ERR_INVALID_ARGUMENT, "moe_down_proj: NULL H / w2p / Y");
   MOE_REQUIRE(T >= 0 && h >= 8 && d >= 8, MOE_ERR_INVALID_ARGUMENT, "moe_down_proj: bad sizes T=%d h=%d d=%d", T, h, d);
+  if (T == 0) return MOE_OK;   // empty tensors have no storage to point at
+  MOE_REQUIRE(H && w2p && Y, MOE_ERR_INVALID_ARGUMENT, "moe_down_proj: NULL H / w2p / Y");
   MOE_REQUIRE(h % 8 == 0 && d % 8 == 0, MOE_ERR_UNSUPPORTED_SHAPE, "moe_down_proj: h=%d and d=%d must be multiples of 8", h, d);
   MOE_REQUIRE((reinterpret_cast<uintptr_t>(Y) & 15) == 0, MOE_ERR_INVALID_ARGUMENT, "moe_down_proj: Y must be 16-byte aligned");
   MOE_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, MOE_ERR_INVALID_ARGUMENT,

@@ -313,9 +313,10 @@ int moe_router_topk_biased(const float* scores, const float* score_bias, const u
                            uint32_t* active_bits, int16_t* idx, unsigned long long* hist, float* score_colmax, void* H,
                            int h, int es, int T, int E, int count_begin, int count_end, void* stream) {
   using namespace moe;
-  MOE_REQUIRE(scores != nullptr, MOE_ERR_INVALID_ARGUMENT, "moe_router_topk: scores is NULL");
   MOE_REQUIRE(T >= 0 && E >= 1 && k >= 0 && k <= E, MOE_ERR_INVALID_ARGUMENT,
               "moe_router_topk: need T>=0, 1<=E, 0<=k<=E (T=%d E=%d k=%d)", T, E, k);
+  if (T == 0) return MOE_OK;   // empty tensors have no storage to point at
+  MOE_REQUIRE(scores != nullptr, MOE_ERR_INVALID_ARGUMENT, "moe_router_topk: scores is NULL");
   MOE_REQUIRE(E <= 1024, MOE_ERR_UNSUPPORTED_SHAPE, "moe_router_topk: E=%d > 1024 experts", E);
   if (H != nullptr) {
     MOE_REQUIRE(es >= 1 && h == E * es && h < 65536, MOE_ERR_INVALID_ARGUMENT,
@@ -386,7 +387,7 @@ static int colmax_grid_y(int rows) {
 
 int moe_colmax_f32(const float* m, int T, int C, float* out, void* stream) {
   using namespace moe;
-  MOE_REQUIRE(m != nullptr && out != nullptr && T >= 0 && C >= 1, MOE_ERR_INVALID_ARGUMENT, "moe_colmax_f32: bad args");
+  MOE_REQUIRE((m != nullptr || T == 0) && out != nullptr && T >= 0 && C >= 1, MOE_ERR_INVALID_ARGUMENT, "moe_colmax_f32: bad args");
   if (T == 0) return MOE_OK;
   dim3 grid((C + 31) / 32, colmax_grid_y(T));
   cudaError_t le = launch_pdl(colmax_kernel<float>, grid, dim3(256), 0, static_cast<cudaStream_t>(stream), m, T, C, out);
@@ -396,7 +397,7 @@ int moe_colmax_f32(const float* m, int T, int C, float* out, void* stream) {
 
 int moe_colmax_bf16(const void* m, int T, int C, float* out, void* stream) {
   using namespace moe;
-  MOE_REQUIRE(m != nullptr && out != nullptr && T >= 0 && C >= 1, MOE_ERR_INVALID_ARGUMENT, "moe_colmax_bf16: bad args");
+  MOE_REQUIRE((m != nullptr || T == 0) && out != nullptr && T >= 0 && C >= 1, MOE_ERR_INVALID_ARGUMENT, "moe_colmax_bf16: bad args");
   if (T == 0) return MOE_OK;
   dim3 grid((C + 31) / 32, colmax_grid_y(T));
   cudaError_t le = launch_pdl(colmax_kernel<__nv_bfloat16>, grid, dim3(256), 0, static_cast<cudaStream_t>(stream),

@@ -79,7 +79,7 @@ extern "C" {
 
 int moe_colsum_f32(const float* m, int T, int C, const uint8_t* row_mask, int period, float* out, void* stream) {
   using namespace moe;
-  MOE_REQUIRE(m != nullptr && out != nullptr && T >= 0 && C >= 1, MOE_ERR_INVALID_ARGUMENT, "moe_colsum_f32: bad args");
+  MOE_REQUIRE((m != nullptr || T == 0) && out != nullptr && T >= 0 && C >= 1, MOE_ERR_INVALID_ARGUMENT, "moe_colsum_f32: bad args");
   MOE_REQUIRE(row_mask == nullptr || period >= 1, MOE_ERR_INVALID_ARGUMENT, "moe_colsum_f32: row_mask needs period >= 1");
   if (T == 0) return MOE_OK;
   const int rows_per_cta = 64;
@@ -92,7 +92,7 @@ int moe_colsum_f32(const float* m, int T, int C, const uint8_t* row_mask, int pe
 
 int moe_rownorm_colsumsq_bf16(const void* H, int T, int h, float* out, void* stream) {
   using namespace moe;
-  MOE_REQUIRE(H != nullptr && out != nullptr && T >= 0 && h >= 8, MOE_ERR_INVALID_ARGUMENT, "moe_rownorm_colsumsq_bf16: bad args");
+  MOE_REQUIRE((H != nullptr || T == 0) && out != nullptr && T >= 0 && h >= 8, MOE_ERR_INVALID_ARGUMENT, "moe_rownorm_colsumsq_bf16: bad args");
   MOE_REQUIRE(h % 8 == 0 && (reinterpret_cast<uintptr_t>(H) & 15) == 0, MOE_ERR_UNSUPPORTED_SHAPE,
               "moe_rownorm_colsumsq_bf16: h=%d must be a multiple of 8 and H 16-byte aligned", h);
   if (T == 0) return MOE_OK;

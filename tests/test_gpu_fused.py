@@ -163,6 +163,28 @@ def test_fused_randomised_against_separate_kernels(lib):
     assert "80 cases, 0 failures" in res.stdout
 
 
+def test_fused_empty_input_is_a_no_op(lib):
+    """Zero tokens (an empty prompt shard): no launch, empty outputs, counters untouched."""
+    from moe_b200.packing import ExpertLayout, pack_ffn
+    layer = O.synthetic_layer(64, 256, (1, 4), 16, seed=2)
+    lay = ExpertLayout.from_labels(layer["labels"])
+    p = pack_ffn(lay, layer["w1"], layer["b1"], layer["w2"], layer["b2"], device=DEV)
+    x = torch.empty(0, 64, dtype=torch.bfloat16, device=DEV)
+    hist = torch.full((lay.n_experts,), 7, dtype=torch.int64, device=DEV)
+    y, H, scores, bits, idx = M.ffn_fused(x, p.w1p, p.b1p, p.w2p, p.b2, lay.n_experts, lay.expert_size, 4, O.ACT_GELU,
+                                          want_bits=True, want_idx=True, hist=hist, count_rows=(0, 0))
+    torch.cuda.synchronize()
+    assert y.shape == (0, 64) and H.shape == (0, 256) and scores.shape == (0, lay.n_experts)
+    assert idx.shape[0] == 0 and bits.shape[0] == 0
+    assert bool((hist == 7).all())
+    # the separate entry points accept the same empty shard
+    H2, sc2, _ = M.geglu_up(x, p.w1p, p.b1p, lay.n_experts, lay.expert_size, O.ACT_GELU)
+    b2, i2 = M.router_topk(sc2, 4, want_bits=True, want_idx=True, hist=hist, H=H2, expert_size=lay.expert_size, count_rows=(0, 0))
+    y2 = M.down_proj(H2, p.w2p, p.b2)
+    torch.cuda.synchronize()
+    assert y2.shape == (0, 64) and i2.shape[0] == 0 and bool((hist == 7).all())
+
+
 def test_fused_unsupported_geometry_raises(lib):
     x = torch.zeros(8, 40, dtype=torch.bfloat16, device=DEV)
     w1 = torch.zeros(320, 40, dtype=torch.bfloat16, device=DEV)
