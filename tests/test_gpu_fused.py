@@ -185,6 +185,18 @@ def test_fused_empty_input_is_a_no_op(lib):
     assert y2.shape == (0, 64) and i2.shape[0] == 0 and bool((hist == 7).all())
 
 
+def test_fused_k_zero_masks_everything(lib):
+    """ratio so small that k = int(E * ratio) = 0 (helper.py:61 allows it): no expert is active, H is all zeros and the
+    output is the down-projection bias."""
+    layer = O.synthetic_layer(320, 1280, (1, 300), 20, seed=5)
+    cu = fused_layer(layer, 0.01)
+    assert cu["k"] == 0
+    assert float(cu["H"].abs().max()) == 0.0
+    assert int(cu["hist"].sum()) == 0 and all(len(s_) == 0 for s_ in cu["sets"])
+    b2 = layer["b2"].to(torch.bfloat16).float()
+    assert torch.equal(cu["y"].reshape(-1, 320), b2.expand(300, 320))
+
+
 def test_fused_unsupported_geometry_raises(lib):
     x = torch.zeros(8, 40, dtype=torch.bfloat16, device=DEV)
     w1 = torch.zeros(320, 40, dtype=torch.bfloat16, device=DEV)
