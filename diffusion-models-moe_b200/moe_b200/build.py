@@ -31,14 +31,25 @@ def sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
-def _digest():
+def _headers():
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")) + \
+        [os.path.join(INCLUDE, "moe_b200.h")]
+
+
+def _file_digest(src):
+    """One translation unit's digest: its own text, every header, the flags."""
     hsh = hashlib.sha256()
-    files = sources() + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh"))
-    files.append(os.path.join(INCLUDE, "moe_b200.h"))
-    for f in files:
+    for f in [src] + _headers():
         with open(f, "rb") as fh:
             hsh.update(fh.read())
     hsh.update(" ".join(NVCC_FLAGS).encode())
+    return hsh.hexdigest()
+
+
+def _digest():
+    hsh = hashlib.sha256()
+    for f in sources():
+        hsh.update(_file_digest(f).encode())
     return hsh.hexdigest()
 
 
@@ -49,21 +60,44 @@ def nvcc_path():
     raise RuntimeError("nvcc not found")
 
 
+def _compile_one(src, force, verbose):
+    """src.cu -> lib/obj<variant>/src.o, skipped when the object's stamp matches (per-file incremental build)."""
+    obj_dir = os.path.join(LIB_DIR, "obj" + _SUFFIX)
+    os.makedirs(obj_dir, exist_ok=True)
+    base = os.path.splitext(os.path.basename(src))[0]
+    obj, stamp = os.path.join(obj_dir, base + ".o"), os.path.join(obj_dir, base + ".stamp")
+    digest = _file_digest(src)
+    if not force and os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read().strip() == digest:
+        return obj, ""
+    flags = [f for f in NVCC_FLAGS if f not in ("--shared",)]
+    cmd = [nvcc_path()] + flags + (["-Xptxas=-v"] if verbose else []) + ["-I", INCLUDE, "-c", "-o", obj, src]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"nvcc failed on {src}:\n" + res.stdout + res.stderr)
+    with open(stamp, "w") as f:
+        f.write(digest)
+    return obj, res.stdout + res.stderr
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every csrc/*.cu for sm_100a (in parallel, one object per file) and link libmoe_b200.so."""
+    from concurrent.futures import ThreadPoolExecutor
     os.makedirs(LIB_DIR, exist_ok=True)
     digest = _digest()
     if not force and os.path.exists(LIB_PATH) and os.path.exists(STAMP):
         if open(STAMP).read().strip() == digest:
             return LIB_PATH
-    cmd = [nvcc_path()] + NVCC_FLAGS + ["-I", INCLUDE, "-o", LIB_PATH] + sources()
+    srcs = sources()
+    with ThreadPoolExecutor(max_workers=min(len(srcs), os.cpu_count() or 1)) as pool:
+        results = list(pool.map(lambda s: _compile_one(s, force, verbose), srcs))
     if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-        print(" ".join(cmd))
-    res = subprocess.run(cmd, capture_output=True, text=True)
+        for _, log in results:
+            if log:
+                print(log)
+    link = [nvcc_path()] + NVCC_FLAGS + ["-o", LIB_PATH] + [obj for obj, _ in results]
+    res = subprocess.run(link, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stdout + res.stderr)
+        raise RuntimeError("nvcc link failed:\n" + res.stdout + res.stderr)
     with open(STAMP, "w") as f:
         f.write(digest)
     return LIB_PATH

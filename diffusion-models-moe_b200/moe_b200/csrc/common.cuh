@@ -55,15 +55,43 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+constexpr int kMaxDevices = 64;
+
+inline int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+  return dev;
+}
+
+// SM count of the CURRENT device (a process may drive several GPUs: every cache below is per device)
 inline int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-      n = 148;  // B200
+  static int n[kMaxDevices] = {0};
+  const int dev = current_device();
+  if (n[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;  // B200
+    n[dev] = v;
   }
-  return n;
+  return n[dev];
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: remember (kernel, device) pairs
+inline int ensure_dynamic_smem(const void* kfn, size_t bytes) {
+  struct Entry { const void* fn; int dev; size_t bytes; };
+  static Entry configured[256];
+  static std::atomic<int> n_configured{0};
+  const int dev = current_device();
+  const int n = n_configured.load(std::memory_order_acquire);
+  for (int i = 0; i < n; ++i)
+    if (configured[i].fn == kfn && configured[i].dev == dev && configured[i].bytes >= bytes) return MOE_OK;
+  cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+  if (e != cudaSuccess) return fail(MOE_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu): %s", bytes, cudaGetErrorString(e));
+  const int slot = n_configured.load(std::memory_order_relaxed);
+  if (slot < 256) {      // (a race between two host threads costs one redundant cudaFuncSetAttribute, nothing else)
+    configured[slot] = Entry{kfn, dev, bytes};
+    n_configured.store(slot + 1, std::memory_order_release);
+  }
+  return MOE_OK;
 }
 
 }  // namespace moe

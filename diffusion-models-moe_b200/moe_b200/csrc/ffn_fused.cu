@@ -1505,15 +1505,86 @@ static int ilog2(int v) {
   return l;
 }
 
-static int ensure_smem(const void* kfn) {
-  static const void* configured[16];
-  static int n_configured = 0;
-  for (int i = 0; i < n_configured; ++i)
-    if (configured[i] == kfn) return MOE_OK;
-  cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
-  if (e != cudaSuccess) return fail(MOE_ERR_CUDA, "cudaFuncSetAttribute(smem=%d): %s", kSmemLimit, cudaGetErrorString(e));
-  if (n_configured < 16) configured[n_configured++] = kfn;
+static int ensure_smem(const void* kfn) { return ensure_dynamic_smem(kfn, kSmemLimit); }   // per (kernel, device)
+
+// The kernel's CTAs wait on one another, so all `clusters` 2-CTA clusters must be able to be resident at once on
+// this device (full-size B200: 74 clusters on 148 SMs; fewer under an MPS active-thread limit or a green context).
+// Asked once per (kernel, device, shared-memory size).
+static int clusters_fit(const void* kfn, cudaLaunchConfig_t* cfg, int clusters) {
+  struct Entry { const void* fn; int dev; size_t smem; int max_clusters; };
+  static Entry cache[64];
+  static std::atomic<int> n_cache{0};
+  const int dev = current_device();
+  const int n = n_cache.load(std::memory_order_acquire);
+  int have = -1;
+  for (int i = 0; i < n; ++i)
+    if (cache[i].fn == kfn && cache[i].dev == dev && cache[i].smem == cfg->dynamicSmemBytes) have = cache[i].max_clusters;
+  if (have < 0) {
+    int mc = 0;
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&mc, kfn, cfg);
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      return fail(MOE_ERR_CUDA, "cudaOccupancyMaxActiveClusters: %s", cudaGetErrorString(e));
+    }
+    have = mc;
+    const int slot = n_cache.load(std::memory_order_relaxed);
+    if (slot < 64) {
+      cache[slot] = Entry{kfn, dev, cfg->dynamicSmemBytes, mc};
+      n_cache.store(slot + 1, std::memory_order_release);
+    }
+  }
+  if (have < clusters)
+    return fail(MOE_ERR_UNSUPPORTED_SHAPE,
+                "moe_ffn_fused: only %d of the %d CTA pairs can be co-resident on this device (reduced-SM context?); "
+                "use the unfused kernels", have, clusters);
   return MOE_OK;
+}
+
+// Two fused launches must never be resident together: each would hold SMs while spinning on CTAs of its own grid
+// that cannot be scheduled.  Launches on ONE stream are ordered anyway (programmatic dependent launch only overlaps
+// the prologue); a launch on a different stream of the same device first waits for an event recorded behind the
+// previous fused launch.  Streams under capture are left alone (cross-stream event waits would be captured as graph
+// edges to work outside the graph): a captured graph serialises its own fused nodes through its stream order.
+struct FusedOrder {
+  cudaEvent_t ev = nullptr;
+  cudaStream_t last = nullptr;
+  bool any = false;
+};
+static FusedOrder g_order[kMaxDevices];
+
+static int order_before_launch(cudaStream_t st) {
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return MOE_OK;
+  }
+  if (cap != cudaStreamCaptureStatusNone) return MOE_OK;
+  FusedOrder& o = g_order[current_device()];
+  if (o.any && o.last != st && o.ev != nullptr) {
+    cudaError_t e = cudaStreamWaitEvent(st, o.ev, 0);
+    if (e != cudaSuccess) return fail(MOE_ERR_CUDA, "moe_ffn_fused: cudaStreamWaitEvent: %s", cudaGetErrorString(e));
+  }
+  return MOE_OK;
+}
+
+static void order_after_launch(cudaStream_t st) {
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) {
+    (void)cudaGetLastError();
+    return;
+  }
+  FusedOrder& o = g_order[current_device()];
+  if (o.ev == nullptr && cudaEventCreateWithFlags(&o.ev, cudaEventDisableTiming) != cudaSuccess) {
+    (void)cudaGetLastError();
+    o.ev = nullptr;
+    return;
+  }
+  if (cudaEventRecord(o.ev, st) == cudaSuccess) {
+    o.last = st;
+    o.any = true;
+  } else {
+    (void)cudaGetLastError();
+  }
 }
 
 }  // namespace fused
@@ -1863,6 +1934,10 @@ int moe_ffn_fused(const void* x, const void* w1p, const float* b1p, const void* 
   do {                                                                                              \
     rc = ensure_smem(reinterpret_cast<const void*>(ffn_fused_kernel<CHV>));                         \
     if (rc) return rc;                                                                              \
+    rc = clusters_fit(reinterpret_cast<const void*>(ffn_fused_kernel<CHV>), &cfg, P);               \
+    if (rc) return rc;                                                                              \
+    rc = order_before_launch(cfg.stream);                                                           \
+    if (rc) return rc;                                                                              \
     le = cudaLaunchKernelEx(&cfg, ffn_fused_kernel<CHV>, tx, tw1, ths, thl, tw2, ty, ths_rem, ty_rem, txres, g, a); \
   } while (0)
   switch (ch1) {
@@ -1874,6 +1949,7 @@ int moe_ffn_fused(const void* x, const void* w1p, const float* b1p, const void* 
   }
 #undef MOE_LAUNCH_FUSED
   if (le != cudaSuccess) return fail(MOE_ERR_CUDA, "moe_ffn_fused launch: %s", cudaGetErrorString(le));
+  order_after_launch(cfg.stream);
   return check_launch("moe_ffn_fused");
 }
 

@@ -870,15 +870,8 @@ static size_t smem_bytes(const GemmShape& g) {
 // opt in to the full 227 KiB of dynamic shared memory, once per kernel (keyed by entry address:
 // all instantiations of one template share a function-pointer TYPE)
 static int ensure_smem(const void* kfn, size_t bytes) {
-  static const void* configured[64];
-  static int n_configured = 0;
   if (bytes > static_cast<size_t>(kSmemLimit)) return fail(MOE_ERR_UNSUPPORTED_SHAPE, "smem request %zu too large", bytes);
-  for (int i = 0; i < n_configured; ++i)
-    if (configured[i] == kfn) return MOE_OK;
-  cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
-  if (e != cudaSuccess) return fail(MOE_ERR_CUDA, "cudaFuncSetAttribute(smem=%d): %s", kSmemLimit, cudaGetErrorString(e));
-  if (n_configured < 64) configured[n_configured++] = kfn;
-  return MOE_OK;
+  return ensure_dynamic_smem(kfn, kSmemLimit);   // per (kernel, device)
 }
 
 template <typename... KArgs, typename... Args>

@@ -139,10 +139,12 @@ def down_proj(H, w2p, b2, out=None):
 _fused_workspaces = {}
 
 
-def fused_workspace(device, nbytes: int) -> torch.Tensor:
-    """Zero-initialised workspace of the fused layer kernel (sync counters + split-K partials), one per device,
-    grown on demand; the kernel leaves its counters at zero (allocate during warm-up, before graph capture)."""
-    key = torch.device(device).index
+def fused_workspace(device, nbytes: int, stream_ptr: int = 0) -> torch.Tensor:
+    """Zero-initialised workspace of the fused layer kernel (sync counters + split-K partials), one per (device,
+    stream), grown on demand; the kernel leaves its counters at zero (allocate during warm-up, before graph capture).
+    Fused launches on different streams of one device never share counters, and the library additionally orders them
+    one after the other (two persistent grids must not be resident together, see moe_b200.h)."""
+    key = (torch.device(device).index, int(stream_ptr))
     ws = _fused_workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.zeros(nbytes, dtype=torch.uint8, device=device)
@@ -184,7 +186,7 @@ def ffn_fused(x, w1p, b1p, w2p, b2, n_experts: int, expert_size: int, k: int, ac
     if hist is not None:
         _need(hist, torch.int64, "hist", (E,))
     with torch.cuda.device(dev):
-        ws = fused_workspace(dev, int(lib.moe_ffn_fused_workspace_bytes(T, d, h)))
+        ws = fused_workspace(dev, int(lib.moe_ffn_fused_workspace_bytes(T, d, h)), _stream(x))
         rc = lib.moe_ffn_fused(_ptr(x), _ptr(w1p), _ptr(b1p), _ptr(w2p), _ptr(b2), _ptr(H), _ptr(scores), _ptr(Y),
                                _ptr(removed_bits), int(k), _ptr(bits), _ptr(idx), _ptr(hist), int(count_rows[0]),
                                int(count_rows[1]), T, d, h, E, int(expert_size), int(act), 1 if mask_h else 0, _ptr(ws),

@@ -25,6 +25,14 @@ class ExpertLayout:
     def hidden(self) -> int:
         return self.n_experts * self.expert_size
 
+    @property
+    def is_identity(self) -> bool:
+        cached = self.__dict__.get("_identity")
+        if cached is None:
+            cached = bool(torch.equal(self.perm, torch.arange(self.hidden)))
+            self.__dict__["_identity"] = cached
+        return cached
+
     @staticmethod
     def from_labels(labels: Sequence[int]) -> "ExpertLayout":
         lab = np.asarray(labels, dtype=np.int64)

@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from neuron_receivers.base_receiver import BaseNeuronReceiver
-from neuron_receivers.moefy import routed_geglu
+from neuron_receivers.moefy import routed_ffn
 
 
 class FrequencyMeasure(BaseNeuronReceiver):
@@ -67,9 +67,9 @@ class FrequencyMeasure(BaseNeuronReceiver):
             hist = self._hist_tensor(x.device)[self.timestep, self.layer, :E]
             rows = (0, seq_len) if self.count_rows == 'row0' else (0, bsz * seq_len)
             self._seq_len[(self.timestep, self.layer)] = seq_len
-        H, _, state, lead = routed_geglu(self, module, x, hist=hist, count_rows=rows)
+        out, _ = routed_ffn(self, module, x, hist=hist, count_rows=rows)
         self.update_time_layer()
-        return self._finish(H, state, lead, x)
+        return out
 
     # -- results ------------------------------------------------------------------------------------
     def int_counts(self) -> torch.Tensor:

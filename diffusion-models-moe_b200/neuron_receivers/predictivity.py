@@ -7,7 +7,7 @@ from moe_b200 import ops
 from moe_b200.ffn import as_tokens, get_state
 from moe_b200.sd_modules import GEGLU, GELU  # noqa: F401
 from moe_b200.stats import StatMeter
-from neuron_receivers.base_receiver import BaseNeuronReceiver
+from neuron_receivers.base_receiver import BaseNeuronReceiver, original_order
 
 
 class NeuronPredictivity(BaseNeuronReceiver):
@@ -35,8 +35,8 @@ class NeuronPredictivity(BaseNeuronReceiver):
             self.max_gate[t] = {l: [] for l in range(self.n_layers)}
 
     def hook_fn(self, module, input, output):
-        """max over all tokens of act(gate) per neuron (predictivity.py:42-53), in the model's
-        neuron order; returns the plain GEGLU output."""
+        """max over all tokens of act(gate) per neuron (predictivity.py:42-53), in the ORIGINAL neuron order
+        (what skilled_neuron_ap.py writes and RemoveNeurons reads back); returns the plain GEGLU output."""
         if self.replace_fn != GEGLU:
             raise NotImplementedError("only GEGLU FFNs are implemented natively")
         x = input[0]
@@ -44,10 +44,7 @@ class NeuronPredictivity(BaseNeuronReceiver):
         lead = x.shape[:-1]
         H, _, gate = ops.geglu_up(as_tokens(x), state.w1p, state.b1p, state.n_experts, state.expert_size, state.act,
                                   want_scores=False, want_gate=True)
-        mx = ops.colmax(gate)
-        if not state.weights_permuted_in_model:
-            mx = mx[state.layout.inv_perm.to(mx.device)]
-        max_act = mx.cpu().numpy()
+        max_act = original_order(ops.colmax(gate), state).cpu().numpy()    # original neuron order, as the reference's
         self.max_gate[self.timestep][self.layer] = max_act
         self.predictivity.update(max_act, self.timestep, self.layer)
         self.update_time_layer()

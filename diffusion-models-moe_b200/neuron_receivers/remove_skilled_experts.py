@@ -11,7 +11,7 @@ import torch
 
 from moe_b200.packing import bits_from_expert_list
 from moe_b200.sd_modules import GEGLU
-from neuron_receivers.moefy import routed_geglu
+from neuron_receivers.moefy import routed_ffn
 from neuron_receivers.predictivity import NeuronPredictivity
 
 REMOVAL_TIMESTEPS = 20  # hard-coded `self.timestep < 20`, remove_skilled_experts.py:32
@@ -55,6 +55,6 @@ class RemoveExperts(NeuronPredictivity):
             if self.hist is not None:
                 hist = self.hist[self.timestep, self.layer, :E]
                 rows = (0, x.shape[1]) if self.count_rows == 'row0' else (0, x.shape[0] * x.shape[1])
-        H, _, state, lead = routed_geglu(self, module, x, removed_bits=removed, hist=hist, count_rows=rows)
+        out, _ = routed_ffn(self, module, x, removed_bits=removed, hist=hist, count_rows=rows)
         self.update_time_layer()
-        return self._finish(H, state, lead, x)
+        return out

@@ -52,16 +52,41 @@ class WandaRemoveNeuronsFast(NeuronPredictivity):
 
     # -- packed masks --------------------------------------------------------------------------------
     def mask_bits(self, t, l, device, column_perm=None):
-        key = (t, l)
-        if key not in self._bits:
-            self._bits[key] = pack_weight_mask(self.expert_indices[t][l], device, column_perm)
-        return self._bits[key]
+        """Packed mask of cell (t, l) on `device`; `column_perm` (the in-place packing of the Linear's columns,
+        `down._moe_column_perm`) is part of the cache key: bits packed for one column order are never served for
+        another."""
+        hit = self._bits.get((t, l))
+        if hit is not None and (isinstance(hit[0], str) or hit[0] is column_perm):
+            return hit[1]
+        bits = pack_weight_mask(self.expert_indices[t][l], device, column_perm)
+        self._bits[(t, l)] = (column_perm, bits)
+        return bits
 
     def set_mask_bits(self, t, l, bits):
-        self._bits[(t, l)] = bits
+        """Install ready-made bit words (already in the column order of the Linear they will meet)."""
+        self._bits[(t, l)] = ('given', bits)
 
     def invalidate(self):
         self._bits = {}
+        self._w_cache = {}
+
+    def remove_hooks(self, hooks):
+        super().remove_hooks(hooks)
+        self._w_cache = {}          # bf16 copies of fp16 / fp32 weights live for one observe_activation
+
+    def _weights(self, module):
+        """bf16 W2 and f32 b2 of the hooked Linear: the parameters themselves when already in those types, else a
+        copy keyed on (module, data pointer, version counter) -- an in-place update (packing, bake, LoRA merge)
+        or a freed-and-reused module never meets a stale copy."""
+        w, b = module.weight, module.bias
+        key = (w.data_ptr(), w._version, None if b is None else (b.data_ptr(), b._version))
+        hit = self._w_cache.get(module)
+        if hit is None or hit[0] != key:
+            w2 = w.detach() if w.dtype == torch.bfloat16 and w.is_contiguous() else w.detach().to(torch.bfloat16).contiguous()
+            b2 = None if b is None else b.detach().float().contiguous()
+            hit = (key, w2, b2)
+            self._w_cache[module] = hit
+        return hit[1], hit[2]
 
     # -- hooks -------------------------------------------------------------------------------------------
     def _select_modules(self, model):
@@ -76,16 +101,7 @@ class WandaRemoveNeuronsFast(NeuronPredictivity):
     def linear_hook_fn(self, module, input, output):
         x = input[0]
         lead = x.shape[:-1]
-        w = module.weight
-        if w.dtype != torch.bfloat16:
-            key = id(module)
-            if key not in self._w_cache:
-                self._w_cache[key] = (w.detach().to(torch.bfloat16).contiguous(),
-                                      None if module.bias is None else module.bias.detach().float().contiguous())
-            w2, b2 = self._w_cache[key]
-        else:
-            w2 = w.detach()
-            b2 = None if module.bias is None else module.bias.detach().float()
+        w2, b2 = self._weights(module)
         geglu_state = getattr(module, '_moe_column_perm', None)
         bits = self.mask_bits(self.timestep, self.layer, x.device, geglu_state)
         w2m = ops.mask_weights(w2, bits)

@@ -18,7 +18,9 @@ class TimeLayerColumnNorm:
     def __init__(self, T, n_layers):
         self.T = T
         self.n_layers = n_layers
-        self.sumsq = {}          # (t, layer) -> f32 [h] device tensor, in the MODEL's neuron order
+        self.sumsq = {}          # (t, layer) -> f32 [h] device tensor, in the kernels' packed neuron order
+        # (t, layer) -> packed -> ORIGINAL order index; get_column_norms() returns original order (the order of the
+        # reference's artefacts and of the masks WandaRemoveNeuronsFast consumes)
         self.perm = {}
 
     def cell(self, t, layer, h, device):
@@ -75,7 +77,7 @@ class Wanda(BaseNeuronReceiver):
         H, _, _ = ops.geglu_up(as_tokens(x), state.w1p, state.b1p, state.n_experts, state.expert_size, state.act,
                                want_scores=False)
         ops.rownorm_colsumsq(H, out=self.predictivity.cell(self.timestep, self.layer, H.shape[-1], H.device))
-        if not state.weights_permuted_in_model:
+        if not state.layout.is_identity:
             self.predictivity.perm[(self.timestep, self.layer)] = state.layout.inv_perm.to(H.device)
         self.update_time_layer()
         return self._finish(H, state, lead, x)

@@ -161,7 +161,7 @@ def case_expert_predictivity(name, d, h, B, S, es, ratio, seed, n_prompts=3):
 
 
 @torch.no_grad()
-def case_remove_experts(name, d, h, B, S, es, ratio, seed, removed, T=22, n_layers=2):
+def case_remove_experts(name, d, h, B, S, es, ratio, seed, removed, T=22, n_layers=2, with_down=False):
     layer = O.synthetic_layer(d, h, (B, S), es, seed)
     mod = make_module(layer, ratio, O.ACT_GELU)
     with tempfile.TemporaryDirectory() as td:
@@ -181,6 +181,10 @@ def case_remove_experts(name, d, h, B, S, es, ratio, seed, removed, T=22, n_laye
         outs[f"H_t{t}_l{l}"] = H.numpy()
         outs[f"bitmask_t{t}_l{l}"] = O.labels_to_bitmask(labels, mod.patterns.shape[0])
         outs[f"score_t{t}_l{l}"] = score.numpy()
+        if with_down:    # what the stock ff.net.2 makes of the hook output (upstream FeedForward: Dropout(0) -> Linear)
+            outs[f"y_t{t}_l{l}"] = O.down_proj(H, layer["w2"], layer["b2"]).numpy()
+    if with_down:
+        outs["w2"], outs["b2"] = layer["w2"].numpy(), layer["b2"].numpy()
     rec.timestep, rec.layer = 0, n_layers - 1
     rec.update_time_layer()
     assert (rec.timestep, rec.layer) == (1, 0)
@@ -412,6 +416,11 @@ def main():
     case_wanda_receiver("wanda_receiver_small", 32, 128, 2, 24, 16, 2)
     # Wanda scoring and the union over timesteps
     case_wanda_scoring("wanda_scoring_small", 64, 256, 0.05, 3)
+    # round 2: geometries the fused layer kernel covers (d, h multiples of 64), for the hook-API tests of moe_ffn_fused
+    case_moefy("moefy_d64_gelu", 64, 256, (2, 96), 16, 0.3, O.ACT_GELU, 6, full=True)
+    case_moefy("moefy_d64_relu", 64, 256, (2, 96), 16, 0.3, O.ACT_RELU, 7, full=True)
+    case_moefy("moefy_d128_es64", 128, 512, (2, 40), 64, 0.5, O.ACT_GELU, 8, full=True)     # BASELINE-literal expert size
+    case_remove_experts("remove_experts_d64", 64, 256, 2, 96, 16, 0.5, 9, removed=[1, 5, 9], with_down=True)
 
 
 if __name__ == "__main__":

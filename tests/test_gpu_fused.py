@@ -114,7 +114,7 @@ def test_fused_repeat_launches_share_workspace(lib):
         assert torch.equal(x["H"], y["H"])
         assert torch.equal(x["y"], y["y"])            # deterministic, including the split-K reduction order
         assert torch.equal(x["hist"], y["hist"])
-    ws = M.fused_workspace(DEV, 1)
+    ws = M.fused_workspace(DEV, 1, torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     sync_bytes = 4 * (32 + 2048 * 32)      # header + per-block records
     assert int(ws[:sync_bytes].view(torch.int32).abs().sum()) == 0

@@ -74,7 +74,7 @@ def test_moefy_hook(lib, golden_dir, name):
     assert rel_err(y[wide], T(g["y"]).reshape(n, -1)[wide]) < 1.5e-2      # + cuBLAS bf16 down-projection
     # captured gate (reference moefy.py:25) is the masked activation, on the host
     assert len(rec.gates) == 1 and rec.gates[0].device.type == "cpu" and rec.gates[0].shape == H.shape
-    gc = rec.gates[0].float()[..., mod._moe_state.layout.inv_perm].reshape(n, -1)
+    gc = rec.gates[0].float().reshape(n, -1)                 # captured gates are in the ORIGINAL neuron order
     assert rel_err(gc[wide], T(g["gate"]).reshape(n, -1)[wide]) < OUT_REL_TOL
     assert bool(torch.all(rec.gates[0] >= 0)) == (int(g["act"]) == O.ACT_RELU)
 
@@ -292,7 +292,7 @@ def test_add_experts_hook(lib, golden_dir, tmp_path):
     for e in experts:
         assert bool(live[:, e].all())
     assert int(live.sum(1).max()) <= kk
-    assert rec.gates and rel_err(unpack_cols(rec.gates[0].to(DEV), mod).reshape(-1, H.shape[-1])[safe],
+    assert rec.gates and rel_err(rec.gates[0].float().reshape(-1, H.shape[-1])[safe],
                                  gate.reshape(-1, H.shape[-1])[safe]) < OUT_REL_TOL
 
 
@@ -307,18 +307,17 @@ def test_wanda_receiver_and_sparsity_measure(lib, golden_dir):
     for x in g["xs"]:
         rec.reset_time_layer()
         H = rec.hook_fn(mod, (T(x).to(DEV, torch.bfloat16),), None)
-    norms = rec.predictivity.get_column_norms()[0][0].numpy()
-    norms = norms if mod._moe_state.weights_permuted_in_model is False else norms[mod._moe_state.layout.inv_perm.numpy()]
+    norms = rec.predictivity.get_column_norms()[0][0].numpy()        # original neuron order
     assert np.allclose(norms, g["column_norms"], rtol=2e-2, atol=2e-3)     # bf16 H vs fp32 reference
     # exact restatement on the kernel's own (bf16) H of the last call
     last = O.wanda_column_sumsq(H.float().cpu())
     one = nr.Wanda(0, 1, 1)
     one.hook_fn(mod, (T(g["xs"][-1]).to(DEV, torch.bfloat16),), None)
-    assert torch.allclose(one.predictivity.sumsq[(0, 0)].cpu(), last, rtol=1e-4, atol=1e-6)
+    assert torch.allclose(one.predictivity.sumsq[(0, 0)].cpu(), last, rtol=1e-4, atol=1e-6)   # (device cells: packed order)
     sp = nr.SparsityMeasure(0)
     Hs = sp.hook_fn(mod, (T(g["xs"][0]).to(DEV, torch.bfloat16),), None)
     assert rel_err(unpack_cols(Hs, mod), T(g["H0"])) < OUT_REL_TOL
-    assert rel_err(unpack_cols(sp.gates[0].to(DEV), mod), T(g["gate0"])) < OUT_REL_TOL
+    assert rel_err(sp.gates[0].float(), T(g["gate0"])) < OUT_REL_TOL
     assert bool(torch.all(sp.gates[0] >= 0)) and 0.3 < sp.zero_fraction() < 0.7      # ReLU: about half exact zeros
 
 
@@ -347,3 +346,242 @@ def test_wanda_scoring_and_union_kernels_bit_exact(lib, golden_dir):
     nb, na = torch.zeros(64, device=DEV), torch.ones(64, device=DEV)
     tb = ws.to_dense(ws.score_masks(flat, [nb], [na], 0.25)[0], 2, 64)
     assert tb[:, :16].all() and not tb[:, 16:].any()
+
+
+# ------------------------------------------------------------------ round 2: the fused kernel BEHIND the hook API
+class _OneBlockUNet(torch.nn.Module):
+    """`transformer_blocks.0.ff.net.{0,2}`: the names the receivers filter on, around ONE FeedForward."""
+
+    def __init__(self, ff):
+        super().__init__()
+        blk = torch.nn.Module()
+        blk.ff = ff
+        self.transformer_blocks = torch.nn.ModuleList([blk])
+
+    def forward(self, x):
+        return self.transformer_blocks[0].ff(x)
+
+
+class _OnePipe:
+    """Pipeline stand-in: `pipe(x_list)` runs the FFN once per entry (= layer calls of consecutive UNet steps)."""
+
+    class Out:
+        def __init__(self, images):
+            self.images = images
+
+    def __init__(self, ff):
+        self.unet = _OneBlockUNet(ff)
+
+    def __call__(self, xs, **kw):
+        return _OnePipe.Out([[self.unet(x) for x in xs]])
+
+
+def _kernel_names(fn):
+    """CUDA kernel names launched by fn() (CUPTI through torch.profiler)."""
+    from torch.profiler import profile, ProfilerActivity
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        fn()
+        torch.cuda.synchronize()
+    return [e.name for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+
+
+@pytest.mark.parametrize("name", ["moefy_d64_gelu", "moefy_d64_relu", "moefy_es20", "moefy_d128_es64"])
+def test_hooked_ffn_is_one_fused_launch_and_matches_reference(lib, golden_dir, name):
+    """through `observe_activation` a routed receiver issues exactly ONE user kernel per layer call
+    (moe_ffn_fused) -- no K1/K2/K3 triple, no cuBLAS down-projection -- and the FFN output matches the reference's."""
+    import moe_b200 as M
+    g = load(golden_dir, name)
+    ff = make_ff(g, float(g["ratio"]))
+    if int(g["act"]) == O.ACT_RELU:
+        ff.net[0].gelu = torch.nn.functional.relu
+    pipe = _OnePipe(ff)
+    x = T(g["x"]).to(DEV, torch.bfloat16)
+    rec = nr.MOEFy(seed=0, capture_gates=False)
+    rec.observe_activation(pipe, [x])                       # warm-up: workspace allocation, kernel attributes
+    M.reset_launch_count()
+    out, gates = rec.observe_activation(pipe, [x, x])
+    torch.cuda.synchronize()
+    assert M.launch_count() == 2 and gates == []            # one launch per layer call
+    y = out[0].float().cpu()
+    wide = (g["margin"] > 0.25).reshape(-1)
+    n = wide.shape[0]
+    assert y.shape == tuple(g["y"].shape)
+    assert rel_err(y.reshape(n, -1)[wide], T(g["y"]).reshape(n, -1)[wide]) < OUT_REL_TOL
+    # the patch is gone: ff.net.2 is the stock Linear again
+    assert "forward" not in ff.net[2].__dict__ and "forward" not in ff.net[0].__dict__
+    assert not ff.net[0]._moe_state.fused_down
+    # kernel list of one hooked call: exactly one of ours, nothing from cuBLAS / CUTLASS
+    try:
+        names = _kernel_names(lambda: rec.observe_activation(pipe, [x]))
+    except Exception as e:      # noqa: BLE001 -- CUPTI unavailable (e.g. another profiler attached)
+        pytest.skip(f"torch.profiler could not collect CUDA kernels: {e}")
+    if not names:
+        pytest.skip("torch.profiler returned no CUDA kernels (CUPTI unavailable)")
+    ours = [k for k in names if "ffn_fused_kernel" in k]
+    lib_gemm = [k for k in names if any(s in k.lower() for s in ("gemm", "cutlass", "cublas", "xmma", "nvjet"))]
+    assert len(ours) == 1 and lib_gemm == [], names
+
+
+def test_hooked_ffn_with_gate_capture_stays_native(lib, golden_dir):
+    """capture_gates (the reference default) needs the activated gate as a tensor: K1 -> K2 -> K2(gate) -> K3, all
+    ours; the gates come back on the host in original neuron order."""
+    import moe_b200 as M
+    g = load(golden_dir, "moefy_d64_gelu")
+    ff = make_ff(g, float(g["ratio"]))
+    pipe = _OnePipe(ff)
+    x = T(g["x"]).to(DEV, torch.bfloat16)
+    rec = nr.MOEFy(seed=0)
+    rec.observe_activation(pipe, [x])
+    M.reset_launch_count()
+    out, gates = rec.observe_activation(pipe, [x])
+    assert M.launch_count() == 4
+    wide = (g["margin"] > 0.25).reshape(-1)
+    n = wide.shape[0]
+    assert rel_err(out[0].float().cpu().reshape(n, -1)[wide], T(g["y"]).reshape(n, -1)[wide]) < OUT_REL_TOL
+    assert len(gates) == 1 and gates[0].device.type == "cpu" and gates[0].is_pinned()
+    assert rel_err(gates[0].float().reshape(n, -1)[wide], T(g["gate"]).reshape(n, -1)[wide]) < OUT_REL_TOL
+    # fused and split paths agree on the FFN output
+    rec2 = nr.MOEFy(seed=0, capture_gates=False)
+    out2, _ = rec2.observe_activation(pipe, [x])
+    assert rel_err(out2[0].float(), out[0].float()) < 2e-3
+
+
+def test_frequency_and_removal_through_fused_hooks(lib, golden_dir, tmp_path):
+    """FrequencyMeasure / RemoveExperts through observe_activation: the fused launch carries the histogram and the
+    removed-expert bits; counts equal the unfused path's bit for bit, the FFN output matches the reference's
+    RemoveExperts.hook_fn followed by the stock down-projection (golden y_t*_l0)."""
+    import moe_b200 as M
+    g = load(golden_dir, "remove_experts_d64")
+    removed = [int(v) for v in g["removed"]]
+    times = [0, 19, 20]                                       # < 20 removes, >= 20 does not
+    for t in range(21):
+        json.dump(removed, open(tmp_path / f"timestep_{t}_layer_0.json", "w"))
+    ff = make_ff(g, float(g["ratio"]))
+    mod = ff.net[0]
+    E = mod.patterns.shape[0]
+    pipe = _OnePipe(ff)
+    x = T(g["x"]).to(DEV, torch.bfloat16)
+    ntok = x.shape[0] * x.shape[1]
+    counts, outs = {}, {}
+    for fuse in (True, False):
+        hist = torch.zeros(21, 1, E, dtype=torch.int64, device=DEV)
+        rec = nr.RemoveExperts(0, str(tmp_path), 21, 1, capture_gates=False, hist=hist, count_rows='all', fuse_down_proj=fuse)
+        rec.observe_activation(pipe, [x])                      # warm-up
+        hist.zero_()
+        M.reset_launch_count()
+        rec.reset_time_layer()
+        out, _ = rec.observe_activation(pipe, [x] * 21)
+        assert (rec.timestep, rec.layer) == (21, 0)
+        assert M.launch_count() == (21 if fuse else 42)        # fused: one launch; unfused: K1 + K2 (+ cuBLAS)
+        counts[fuse] = hist.cpu().numpy()
+        outs[fuse] = [o.float().cpu() for o in out]
+    assert np.array_equal(counts[True], counts[False])
+    assert counts[True].sum(-1).reshape(-1).tolist() == [ntok * mod.k] * 21
+    for t in times:
+        score = T(g[f"score_t{t}_l0"])
+        wide = (O.topk_margin(score, mod.k) > 0.25).numpy()
+        assert wide.mean() > 0.3
+        yr = T(g[f"y_t{t}_l0"]).reshape(ntok, -1)
+        for fuse in (True, False):
+            assert rel_err(outs[fuse][t].reshape(ntok, -1)[wide], yr[wide]) < (OUT_REL_TOL if fuse else 1.5e-2), (t, fuse)
+        # oracle on the bf16-rounded inputs, every token whose margin exceeds 2e-3
+        pat = O.patterns_from_labels(g["labels"])
+        H, _, _, sc = O.remove_experts_forward(r16(T(g["x"])), r16(T(g["w1"])), T(g["b1"]), pat, mod.k, removed, t)
+        safe = (O.topk_margin(sc, mod.k) > 2e-3).numpy()
+        yo = O.down_proj(r16(H), r16(T(g["w2"])), T(g["b2"])).reshape(ntok, -1)
+        assert rel_err(outs[True][t].reshape(ntok, -1)[safe], yo[safe]) < OUT_REL_TOL
+    names = ["l0"]
+    fm = nr.FrequencyMeasure(0, 3, 1, {"l0": E}, names)
+    fm.observe_activation(pipe, [x, x, x])
+    fm2 = nr.FrequencyMeasure(0, 3, 1, {"l0": E}, names, fuse_down_proj=False)
+    fm2.observe_activation(pipe, [x, x, x])
+    assert torch.equal(fm.int_counts(), fm2.int_counts()) and int(fm.int_counts()[0].sum()) == x.shape[1] * mod.k
+
+
+def test_unrouted_receivers_use_the_native_down_projection(lib, golden_dir):
+    """ExpertPredictivity / NeuronPredictivity through observe_activation: K1 (+ statistic) + native K3 -> Y."""
+    import moe_b200 as M
+    g = load(golden_dir, "moefy_d64_gelu")
+    ff = make_ff(g, float(g["ratio"]))
+    pipe = _OnePipe(ff)
+    x = T(g["x"]).to(DEV, torch.bfloat16)
+    dense = ff(x).float()
+    rec = nr.ExpertPredictivity(0, 1, 1)
+    out, _ = rec.observe_activation(pipe, [x])
+    assert out[0].shape == dense.shape and rel_err(out[0].float(), dense) < 1.5e-2       # unmasked FFN
+    rec = nr.NeuronPredictivity(0, 1, 1)
+    M.reset_launch_count()
+    out, _ = rec.observe_activation(pipe, [x])
+    assert M.launch_count() == 3                                   # K1, colmax, K3
+    assert rel_err(out[0].float(), dense) < 1.5e-2
+
+
+def test_neuron_artefacts_round_trip_on_a_permuted_model(lib, tmp_path):
+    """per-neuron results must come back in ORIGINAL neuron order on a model MoEfied with
+    permute_model_weights=True, so that NeuronPredictivity -> JSON -> RemoveNeurons ablates the right neurons."""
+    torch.manual_seed(0)
+    d, h, S = 64, 256, 96
+    layer = O.synthetic_layer(d, h, (2, S), 16, seed=11)
+    g = dict(w1=layer["w1"].numpy(), b1=layer["b1"].numpy(), w2=layer["w2"].numpy(), b2=layer["b2"].numpy(),
+             labels=layer["labels"])
+    ff = make_ff(g, 0.5)
+    assert ff.net[0]._moe_state.weights_permuted_in_model and not ff.net[0]._moe_state.layout.is_identity
+    pipe = _OnePipe(ff)
+    x = layer["x"].to(DEV, torch.bfloat16)
+    x16, w1, w2 = r16(layer["x"]), r16(layer["w1"]), r16(layer["w2"])
+    rec = nr.NeuronPredictivity(0, 1, 1)
+    rec.observe_activation(pipe, [x])
+    _, gate = O.geglu_up(x16, w1, layer["b1"])
+    want_max = O.neuron_predictivity(gate)
+    got_max = np.asarray(rec.max_gate[0][0])
+    assert np.allclose(got_max, want_max, atol=2e-2, rtol=2e-2)             # ORIGINAL order
+    # the "skilled" neurons: the 24 with the largest max activation (stand-in for skilled_neuron_ap.py:171-177)
+    flags = np.zeros(h)
+    flags[np.argsort(got_max)[-24:]] = 1.0
+    json.dump(flags.tolist(), open(tmp_path / "predictivity_0_0.json", "w"))
+    rn = nr.RemoveNeurons(0, str(tmp_path), 1, 1)
+    out, gates = rn.observe_activation(pipe, [x])
+    Ho = O.remove_neurons_forward(x16, w1, layer["b1"], flags.tolist())
+    Ho = Ho[0] if isinstance(Ho, tuple) else Ho
+    yo = O.down_proj(r16(Ho), w2, layer["b2"])
+    assert rel_err(out[0].float().cpu(), yo) < OUT_REL_TOL
+    idx = np.nonzero(flags)[0]
+    assert torch.all(gates[0][..., idx].float() == torch.tensor(-0.17).bfloat16().float())       # original order
+
+
+def test_wanda_artefacts_round_trip_on_a_permuted_model(lib, tmp_path):
+    """Wanda norms -> score_masks -> CSR pickle -> WandaRemoveNeuronsFast on a permuted model
+    masks the same weights the reference would (all artefacts in original column order)."""
+    from moefication import wanda_scoring as ws
+    torch.manual_seed(1)
+    d, h, S = 64, 256, 96
+    layer = O.synthetic_layer(d, h, (2, S), 16, seed=12)
+    adj = O.synthetic_layer(d, h, (2, S), 16, seed=13)
+    g = dict(w1=layer["w1"].numpy(), b1=layer["b1"].numpy(), w2=layer["w2"].numpy(), b2=layer["b2"].numpy(),
+             labels=layer["labels"])
+    ff = make_ff(g, 0.5)
+    pipe = _OnePipe(ff)
+    w1, w2 = r16(layer["w1"]), r16(layer["w2"])
+    norms = {}
+    for tag, xin in (("base", layer["x"]), ("adj", adj["x"] * 1.5)):
+        rec = nr.Wanda(0, 1, 1)
+        rec.observe_activation(pipe, [xin.to(DEV, torch.bfloat16)])
+        norms[tag] = rec.predictivity.get_column_norms()[0][0]
+        v, gt = O.geglu_up(r16(xin), w1, layer["b1"])
+        want = torch.sqrt(O.wanda_column_sumsq((v * gt).reshape(-1, h)))
+        assert torch.allclose(norms[tag], want, rtol=3e-2, atol=3e-3)              # ORIGINAL order
+    bits = ws.score_masks(ff.net[2], [norms["base"].to(DEV)], [norms["adj"].to(DEV)], 0.05)
+    dense = ws.to_dense(bits[0], d, h)
+    # the oracle's mask from the ORIGINAL weight and the receiver's norms: identical bits where the row top-k is not tied
+    want_mask = O.wanda_score_mask(w2.abs(), norms["base"], norms["adj"], 0.05)
+    assert (dense != want_mask).mean() < 2e-3
+    with open(tmp_path / "timestep_0_layer_0.pkl", "wb") as f:
+        pickle.dump(ws.to_csr(bits[0], d, h), f)
+    wr = nr.WandaRemoveNeuronsFast(0, str(tmp_path), 1, 1)
+    x = layer["x"].to(DEV, torch.bfloat16)
+    out, _ = wr.observe_activation(pipe, [x])
+    v, gt = O.geglu_up(r16(layer["x"]), w1, layer["b1"])
+    yo = O.wanda_down_proj(r16(v * gt), w2, layer["b2"], torch.from_numpy(dense))
+    assert rel_err(out[0][0].float().cpu(), yo) < 1.5e-2        # stock (cuBLAS) GEGLU + native masked down-projection
+    y_unmasked = O.down_proj(r16(v * gt), w2, layer["b2"])
+    assert rel_err(out[0][0].float().cpu(), y_unmasked) > rel_err(out[0][0].float().cpu(), yo) * 2

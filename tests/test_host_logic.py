@@ -238,3 +238,85 @@ def test_average_expert_counters_matches_reference_accumulation():
     for t in range(3):
         for n in names:
             assert got[t][n] == want[t][n]
+
+
+def _moe_reference_output(ff_dense, labels, ratio, x):
+    """The oracle's MoEfied FFN on the ORIGINAL (unpermuted) weights of a FeedForward."""
+    g, lin = ff_dense.net[0], ff_dense.net[2]
+    pat = O.patterns_from_labels(labels)
+    H, lab, _, _ = O.moefy_forward(x, g.proj.weight.detach(), g.proj.bias.detach(), pat, int(pat.shape[0] * ratio))
+    return O.down_proj(H, lin.weight.detach(), lin.bias.detach()), lab
+
+
+def test_modify_ffn_without_down_projection_leaves_the_model_alone():
+    """`helper.modify_ffn(ffn, path, k)` -- the reference's exact signature, no down-projection handed
+    over -- must not permute W1 in place (ff.net.2 would then meet packed H with unpermuted columns)."""
+    torch.manual_seed(1)
+    ff = FeedForward(32)
+    w1_before = ff.net[0].proj.weight.detach().clone()
+    labels = O.balanced_labels(128, 16, seed=2)
+    st = helper.modify_ffn(ff.net[0], [int(v) for v in labels], 0.5)
+    assert not st.weights_permuted_in_model and st.applied_perm is None
+    assert torch.equal(ff.net[0].proj.weight, w1_before)
+    # patterns refer to the module's (original) neuron order, exactly the reference's one-hot matrix
+    assert torch.equal(ff.net[0].patterns, O.patterns_from_labels(labels))
+    # the kernels' packed copy has expert e's neurons at [16 e, 16 e + 16)
+    lay = st.layout
+    assert torch.equal(st.w1p[:128].float(), w1_before[:128][lay.perm].bfloat16().float())
+
+
+def test_modify_ffn_twice_is_idempotent_on_the_model():
+    """re-attaching (new top-k / new labels) must not permute already-packed weights again."""
+    torch.manual_seed(2)
+    ff = FeedForward(32)
+    x = torch.randn(2, 7, 32)
+    y_dense = ff(x)
+    w1_orig = ff.net[0].proj.weight.detach().clone()
+    w2_orig = ff.net[2].weight.detach().clone()
+    lab_a = [int(v) for v in O.balanced_labels(128, 16, seed=3)]
+    lab_b = [int(v) for v in O.balanced_labels(128, 16, seed=4)]
+    helper.modify_ffn(ff.net[0], lab_a, 0.5, down=ff.net[2])
+    helper.modify_ffn(ff.net[0], lab_a, 0.25, down=ff.net[2])         # same labels, new ratio
+    st = ff.net[0]._moe_state
+    lay = st.layout
+    assert ff.net[0].k == 2 and st.k == 2 and st.weights_permuted_in_model
+    assert torch.equal(ff.net[0].proj.weight[:128], w1_orig[:128][lay.perm])      # packed ONCE from the original
+    assert torch.equal(ff.net[2].weight, w2_orig[:, lay.perm])
+    assert torch.allclose(ff(x), y_dense, atol=1e-5)
+    helper.modify_ffn(ff.net[0], lab_b, 0.5, down=ff.net[2])          # different labels
+    lay_b = ff.net[0]._moe_state.layout
+    assert torch.equal(ff.net[0].proj.weight[:128], w1_orig[:128][lay_b.perm])
+    assert torch.equal(ff.net[2]._moe_column_perm, lay_b.perm)
+    assert torch.allclose(ff(x), y_dense, atol=1e-5)
+    from moe_b200.ffn import undo_model_permutation
+    undo_model_permutation(ff.net[0])
+    assert torch.equal(ff.net[0].proj.weight, w1_orig) and torch.equal(ff.net[2].weight, w2_orig)
+
+
+def test_packed_copies_follow_parameter_updates():
+    """fp32 parameters are copied to bf16 for the kernels; an in-place update must not leave a stale copy."""
+    from moe_b200.ffn import get_state
+    torch.manual_seed(3)
+    ff = FeedForward(32)
+    helper.modify_ffn(ff.net[0], [int(v) for v in O.balanced_labels(128, 16, seed=5)], 0.5, down=ff.net[2])
+    st = get_state(ff.net[0])
+    before = st.w2p.clone()
+    with torch.no_grad():
+        ff.net[2].weight.mul_(0.5)
+    st2 = get_state(ff.net[0])
+    assert st2 is st and torch.equal(st.w2p.float(), (before.float() * 0.5).bfloat16().float())
+    # activation probe is cached on the identity of module.gelu and redone when it is swapped
+    assert st.act == ops.ACT_GELU
+    ff.net[0].gelu = torch.nn.functional.relu
+    assert get_state(ff.net[0]).act == ops.ACT_RELU
+
+
+def test_fused_down_projection_patch_is_undone():
+    """While hooked, ff.net.2 of a CUDA model is a pass-through; on a CPU model (no kernels) nothing is patched."""
+    unet = _tiny_unet()
+    rec = nr.MOEFy(0, capture_gates=False)
+    hooks = rec.register_hooks(_Pipe(unet))
+    downs = [unet.transformer_blocks[i].ff.net[2] for i in range(2)]
+    assert all("forward" not in d.__dict__ for d in downs)           # CPU weights: the reference flow is kept
+    rec.remove_hooks(hooks)
+    assert rec._fused_states == [] and all(not m._moe_state.fused_down for m in unet.modules() if isinstance(m, GEGLU))
