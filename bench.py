@@ -15,11 +15,20 @@ states and random-init weights of the SD-1.5 geometry.
             the FFNs run through the C ABI, outputs + histogram are copied back (all inside the timing); copy-in,
             compute and copy-out run on three streams chained per layer, consecutive steps pipelined (PCIe-bound:
             tools/pcie_probe.py measures the two-direction copy ceiling for the same bytes).
-  roofline  dominant kernel (ffn_fused_kernel): algorithmic FLOPs (6 d h per token) / CUDA-event time of its launches.
+  roofline  dominant kernel (ffn_fused_kernel): algorithmic FLOPs (6 d h per token) / CUDA-event time of its launches,
+            against the burst bf16 peak of MEASURED_PEAKS.json (sustained peak when the sampled clocks show a power
+            cap); `frac_necessary` counts the down-projection at 2 d es k (active experts only).
+  roofline_router / roofline_hist   K2 router_topk_kernel and K4 hist_accumulate_kernel at the UNet-batch-16 shapes
+            (BASELINE configs[2]): algorithmic bytes / CUDA-event time against the measured HBM copy bandwidth.
+  sampling  BASELINE configs[2] / [3]: 50-step sampling, 8 prompts per batch (UNet batch 16), THROUGH the receiver
+            hook API (RemoveExperts with skilled-expert lists for t < 20 + per-timestep expert counters), each
+            sampling run one CUDA graph captured through the hooks; prompt batches sharded r::W over the ranks, one
+            int64 all-reduce of the [50, 16, 256] histogram at the end, inside the timing.
   cpu_baseline  the oracle port of the reference's hook arithmetic (fp32 torch-CPU, all host threads), timed
-            here on rank 0 at N=1 on a bounded sample (one layer per distinct shape x multiplicity).
-  --impl reference  times that CPU arm alone for K steps (the reference is pure Python on ATen and cannot be
-            installed without diffusers; the oracle port is bit-identical to it on CPU, see oracle/).
+            here on rank 0 at N=1 on a bounded sample (ONE step = all 16 layers).
+  --impl reference  times that CPU arm alone for K steps, all 16 layers every step (the reference is pure Python on
+            ATen and needs diffusers and /root/reference, neither of which exists on the GPU box; the oracle port is
+            bit-identical to the reference classes on CPU -- oracle/gen_golden.py asserts it).
 """
 import argparse
 import json
@@ -27,6 +36,7 @@ import os
 import statistics
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -67,47 +77,74 @@ def parse():
     ap.add_argument("--e2e-groups", type=int, default=2, help="copy groups per step in the e2e leg (1..16)")
     ap.add_argument("--path", default="fused", choices=["fused", "split"],
                     help="fused: one moe_ffn_fused launch per layer; split: K1 -> K2 -> K3 launches")
+    ap.add_argument("--sampling-batches", type=int, default=2,
+                    help="prompt batches (8 prompts x 50 steps each) per rank in the sampling leg; 0 = skip")
+    ap.add_argument("--sampling-steps", type=int, default=50)
+    ap.add_argument("--sampling-prompts", type=int, default=8, help="prompts per batch (UNet batch = 2 x prompts)")
+    ap.add_argument("--no-aux", action="store_true", help="skip the router / histogram roofline legs")
     return ap.parse_args()
+
+
+def workload_config(args, world):
+    """The workload, identically worded for both arms (the driver compares the two `config` objects)."""
+    tokens = args.batch * sum(s for _, _, s in layer_list())
+    return dict(workload="SD-1.5 MoEfied UNet, all 16 transformer-block FFNs, one denoising step, "
+                         f"batch {args.batch} (CFG), 64x64 latents (BASELINE configs[1])",
+                experts=f"{args.experts}: expert_size {expert_size_for(args.experts, 1280)} @h=1280, top-k ratio {RATIO}",
+                tokens_per_step_per_gpu=tokens, parallelism=f"prompt-sharded x{world}",
+                l2="working set ~0.5 GB per step > 126 MB L2; no explicit flush",
+                counters="row-0 expert-selection histogram per layer call")
 
 
 # --------------------------------------------------------------------------------------- CPU arm
 def cpu_arm(args, steps, warmup):
-    """The reference's hook arithmetic (oracle port) on the host cores.  One step = the 16-layer sweep,
-    evaluated as one layer per distinct shape x its multiplicity (identical shapes cost the same)."""
+    """The reference's hook arithmetic (oracle port) on the host cores.  One step = ALL 16 layers of the sweep, each
+    with its own weights and inputs; per layer call the reference pays (a) the stock GEGLU forward whose result the
+    forward hook discards, (b) the hook (MOEFy.hook_fn + counters) and (c) the stock
+    down-projection.  `value` counts (b) + (c) only -- the arithmetic our kernels replace; `with_stock_forward`
+    adds (a), what a user of the reference really waits for."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import moe_ffn_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    shapes = {}
-    for d, h, s in layer_list():
-        shapes[(d, h, s)] = shapes.get((d, h, s), 0) + 1
     layers = []
-    for (d, h, s), mult in shapes.items():
+    for li, (d, h, s) in enumerate(layer_list()):
         es = expert_size_for(args.experts, h)
-        layer = O.synthetic_layer(d, h, (args.batch, s), es, seed=d + s)
+        layer = O.synthetic_layer(d, h, (args.batch, s), es, seed=100 + li)
         pat = O.patterns_from_labels(layer["labels"])
-        layers.append((layer, pat, O.topk_from_ratio(pat.shape[0], RATIO), mult))
+        layers.append((layer, pat, O.topk_from_ratio(pat.shape[0], RATIO)))
     tokens_per_step = args.batch * sum(s for _, _, s in layer_list())
 
     def step():
-        total = 0.0
-        for layer, pat, k, mult in layers:
-            t0 = time.perf_counter()
+        t_hook = t_stock = 0.0
+        for layer, pat, k in layers:
             with torch.no_grad():
+                t0 = time.perf_counter()
+                v, g = O.geglu_up(layer["x"], layer["w1"], layer["b1"])     # stock GEGLU.forward, discarded by the hook
+                _ = v * g
+                t1 = time.perf_counter()
                 H, labels, _, _ = O.moefy_forward(layer["x"], layer["w1"], layer["b1"], pat, k)
                 O.down_proj(H, layer["w2"], layer["b2"])
                 O.selection_counts(labels, pat.shape[0])
-            total += (time.perf_counter() - t0) * mult
-        return total
+                t2 = time.perf_counter()
+            t_stock += t1 - t0
+            t_hook += t2 - t1
+        return t_hook, t_stock
 
     for _ in range(warmup):
         step()
+    wall0 = time.perf_counter()
     times = [step() for _ in range(steps)]
-    sec = statistics.median(times)
-    return dict(value=tokens_per_step / sec, unit="tokens/s", cores=cores, kind="port",
-                sample=f"{steps} x (one layer per distinct shape x multiplicity = 16-layer sweep, batch {args.batch}); "
-                       "oracle.moefy_forward + down_proj + counts, fp32 torch-CPU; median",
-                ms_per_step=sec * 1e3), tokens_per_step
+    wall = time.perf_counter() - wall0
+    hook = statistics.median(t[0] for t in times)
+    both = statistics.median(t[0] + t[1] for t in times)
+    return dict(value=tokens_per_step / hook, unit="tokens/s", cores=cores, kind="port",
+                sample=f"{steps} steps x all 16 layers (own weights and inputs each), batch {args.batch}; "
+                       "oracle.moefy_forward + down_proj + counts, fp32 torch-CPU, median step",
+                ms_per_step=hook * 1e3,
+                with_stock_forward=dict(value=tokens_per_step / both, unit="tokens/s", ms_per_step=both * 1e3,
+                                        note="+ the stock GEGLU forward the reference's forward hook discards"),
+                timed_region_s=wall), tokens_per_step
 
 
 # --------------------------------------------------------------------------------------- clocks
@@ -178,6 +215,181 @@ def bind_to_gpu_numa_node(index):
         return f"gpu {bdf} node {node}: {len(allowed)} cpus allowed, no narrowing"
     except Exception as e:      # noqa: BLE001 -- sysfs layout differs between hosts; the bench runs unbound then
         return f"unbound ({type(e).__name__})"
+
+
+def graph_of(fn, dev):
+    """Capture fn() (already warmed up) on a side stream; returns the replayable graph."""
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        fn()
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g, stream=side):
+            fn()
+    torch.cuda.current_stream().wait_stream(side)
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    return g
+
+
+def time_graph(g, n):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(n):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n      # ms per replay
+
+
+def aux_rooflines(M, args, dev, hbm_gbs, peak_src):
+    """K2 router_topk_kernel and K4 hist_accumulate_kernel against HBM at the UNet-batch-16 shapes (BASELINE
+    configs[2]): the 16 layers' score / hidden-state buffers total 1.6 GB, far beyond L2, so every launch streams from
+    and to HBM.  Algorithmic bytes per token: K2 reads 4 E (scores), writes 2 k (labels) and the
+    zero stores of the masking, 2 es (E - k); K4 reads 2 k (labels).  Times: CUDA events around a graph holding
+    exactly those 16 launches."""
+    B = 16
+    gen = torch.Generator(device=dev).manual_seed(7)
+    cells = []
+    for (d, h, s) in layer_list():
+        es = expert_size_for(args.experts, h)
+        E, T = h // es, B * s
+        k = int(E * RATIO)
+        scores = torch.randn(T, E, generator=gen, device=dev)
+        H = torch.empty(T, h, dtype=torch.bfloat16, device=dev).normal_(generator=gen)
+        cells.append(dict(T=T, E=E, es=es, k=k, scores=scores, H=H, hist=torch.zeros(E, dtype=torch.int64, device=dev), s=s))
+
+    def router():
+        for c in cells:
+            M.router_topk(c["scores"], c["k"], want_bits=False, want_idx=False, hist=c["hist"], H=c["H"],
+                          expert_size=c["es"], count_rows=(0, c["s"]))
+
+    router()
+    torch.cuda.synchronize()
+    ms = time_graph(graph_of(router, dev), 10)
+    by = sum(c["T"] * (4 * c["E"] + 2 * c["es"] * (c["E"] - c["k"])) for c in cells)
+    r_router = dict(bound="hbm", kernel="router_topk_kernel (K2: select + histogram + write-only masking of H)",
+                    achieved=round(by / (ms * 1e-3) / 1e9, 1), peak=hbm_gbs, unit="GB/s",
+                    frac=round(by / (ms * 1e-3) / 1e9 / hbm_gbs, 4), traffic=None, peak_source=peak_src,
+                    algorithmic="per token 4E bytes of scores read + 2 es (E - k) bytes of zero stores; 16 launches at UNet "
+                                f"batch {B} = {by / 1e6:.0f} MB per sweep", ms_per_sweep=round(ms, 4))
+    # select-only form (labels out, no masking): what the permutation / grouped down-projection path consumes
+    idx = []
+
+    def select():
+        idx.clear()
+        for c in cells:
+            _, ix = M.router_topk(c["scores"], c["k"], want_bits=False, want_idx=True)
+            idx.append(ix)
+
+    select()
+    torch.cuda.synchronize()
+    labels = [ix.clone() for ix in idx]
+    ms_sel = time_graph(graph_of(select, dev), 10)
+    by_sel = sum(c["T"] * (4 * c["E"] + 2 * c["k"]) for c in cells)
+    r_router["select_only"] = dict(achieved=round(by_sel / (ms_sel * 1e-3) / 1e9, 1), unit="GB/s",
+                                   frac=round(by_sel / (ms_sel * 1e-3) / 1e9 / hbm_gbs, 4), ms_per_sweep=round(ms_sel, 4),
+                                   algorithmic=f"per token 4E read + 2k labels written = {by_sel / 1e6:.0f} MB per sweep "
+                                               "(working set 0.2 GB > L2)")
+    # K4 over the labels of 24 prompt batches of the d=320 layers (configs[3] accumulation): 0.36 GB of int16 labels
+    big = labels[0].repeat(24, 1)
+    hist = torch.zeros(cells[0]["E"], dtype=torch.int64, device=dev)
+
+    def hist_fn():
+        M.hist_accumulate(big, cells[0]["E"], hist)
+        for c, ix in zip(cells, labels):
+            M.hist_accumulate(ix, c["E"], c["hist"])
+
+    hist_fn()
+    torch.cuda.synchronize()
+    ms_h = time_graph(graph_of(hist_fn, dev), 10)
+    by_h = big.numel() * 2 + sum(ix.numel() * 2 for ix in labels)
+    r_hist = dict(bound="hbm", kernel="hist_accumulate_kernel (K4)", achieved=round(by_h / (ms_h * 1e-3) / 1e9, 1),
+                  peak=hbm_gbs, unit="GB/s", frac=round(by_h / (ms_h * 1e-3) / 1e9 / hbm_gbs, 4), traffic=None,
+                  peak_source=peak_src, ms_per_sweep=round(ms_h, 4),
+                  algorithmic=f"2 bytes per (token, slot) label read: {by_h / 1e6:.0f} MB per sweep (one 0.36 GB label "
+                              "buffer = 24 prompt batches of a d=320 layer, + the 16 per-layer buffers of one batch-16 step)")
+    return r_router, r_hist
+
+
+def sampling_leg(M, args, dev, rank, world, dist):
+    """BASELINE configs[2] / [3] through the receiver API: RemoveExperts (lists for t < 20) + per-timestep counters,
+    8 prompts x 50 steps per CUDA-graph replay; prompt batches b = rank, rank + world, ...; one all-reduce at the end."""
+    import numpy as np
+    import neuron_receivers as nr
+    from moefication import helper
+    from moe_b200.sd_modules import FFNStackUNet, SyntheticFFNPipeline, GraphedSampling, sd_ffn_shapes
+    steps, n_prompts = args.sampling_steps, args.sampling_prompts
+    torch.manual_seed(0)
+    unet = FFNStackUNet(latent_hw=64)
+    pipe = SyntheticFFNPipeline(unet, num_inference_steps=steps, device=dev)
+    shapes = sd_ffn_shapes(64)
+    labels = {}
+    for i, (n, d, h, s) in enumerate(shapes):
+        es = expert_size_for(args.experts, h)
+        labels[n + ".proj.weight"] = np.random.RandomState(i).permutation(np.repeat(np.arange(h // es), es))
+
+    class A:
+        res_path = ""
+        moefication = {"topk_experts": RATIO}
+    pipe, names, n_exp = helper.modify_ffn_to_experts(pipe, A(), labels_by_name=labels)
+    e_max = max(n_exp.values())
+    hist = torch.zeros(steps, 16, e_max, dtype=torch.int64, device=dev)
+    with tempfile.TemporaryDirectory() as td:
+        rs = np.random.RandomState(2)                       # SURVEY section 8(d) config 3: choice(E, E // 10) for t < 20
+        for t in range(steps):
+            for l, nm in enumerate(names):
+                E = n_exp[nm]
+                lst = sorted(int(v) for v in rs.choice(E, E // 10, replace=False)) if t < 20 else []
+                json.dump(lst, open(os.path.join(td, f"timestep_{t}_layer_{l}.json"), "w"))
+        rec = nr.RemoveExperts(0, td, steps, 16, capture_gates=False, hist=hist, count_rows='row0')
+    M.reset_launch_count()
+    gs = GraphedSampling(pipe, rec, n_prompts, steps)
+    launches_per_run = M.launch_count() // 2                # eager pass + capture pass
+    hist.zero_()
+    n_batches = args.sampling_batches
+    # warm replay
+    gs.load_states(10_000 + rank)
+    gs.replay()
+    torch.cuda.synchronize()
+    hist.zero_()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for b in range(n_batches):
+        gs.load_states(rank + b * world)                    # prompt batch index = its seed: rank-independent inputs
+        gs.replay()
+    if world > 1:
+        dist.all_reduce(hist, op=dist.ReduceOp.SUM)
+    hist_host = hist.cpu()                                  # the result a caller reads (freq_expert_select.py:61-72)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms = float(t_ms[0])
+    tok_row0 = [s for (_, _, _, s) in shapes]
+    ks = [int(n_exp[nm] * RATIO) for nm in names]
+    want = torch.tensor([[world * n_batches * tok_row0[l] * ks[l] for l in range(16)]] * steps)
+    exact = bool((hist_host.sum(-1) == want).all())
+    total_steps = world * n_batches * steps
+    tokens = 2 * n_prompts * sum(tok_row0)
+    return dict(config="BASELINE configs[2]/[3]: 50-step sampling of the 16-FFN stack, 8 prompts per batch (UNet batch 16), "
+                       "RemoveExperts lists (10% of the experts, t < 20) + row-0 expert counters per (timestep, layer), "
+                       "through neuron_receivers.RemoveExperts hooks; one CUDA graph per sampling run",
+                ffn_stack_steps_per_s=total_steps / (ms * 1e-3), prompts_per_s=world * n_batches * n_prompts / (ms * 1e-3),
+                tokens_per_s=total_steps * tokens / (ms * 1e-3), ms_per_step=ms / (n_batches * steps),
+                prompt_batches_per_rank=n_batches, steps=steps, unet_batch=2 * n_prompts, n_gpus=world,
+                fused_launches_per_sampling_run=launches_per_run, histogram_counts_exact=exact,
+                timing="CUDA events around load-states + graph replays + all-reduce + D2H of the histogram; max over ranks",
+                note="FFN-stack steps (norm3 + FFN + residual of the 16 transformer blocks, stock LayerNorm / add around "
+                     "our fused launch); conv / attention layers of the UNet are outside this path")
 
 
 def gpu_arm(args):
@@ -268,20 +480,7 @@ def gpu_arm(args):
     torch.cuda.synchronize()
     launches_per_step = (1 if fused else 3) * len(layers)
 
-    graph = None
-    if not args.no_graph:
-        graph = torch.cuda.CUDAGraph()
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            ffn_step()
-            torch.cuda.synchronize()
-            with torch.cuda.graph(graph, stream=side):
-                ffn_step()
-        torch.cuda.current_stream().wait_stream(side)
-        for _ in range(3):
-            graph.replay()
-        torch.cuda.synchronize()
+    graph = None if args.no_graph else graph_of(ffn_step, dev)
 
     def run_step():
         if graph is not None:
@@ -314,6 +513,7 @@ def gpu_arm(args):
     # would time host launch gaps, not the kernels).  Buffers hold valid data from the runs above.
     k1_flops = sum(4.0 * L["d"] * L["h"] * L["T"] for L in layers)
     k3_flops = sum(2.0 * L["d"] * L["h"] * L["T"] for L in layers)
+    k3_necessary = sum(2.0 * L["d"] * L["es"] * L["k"] * L["T"] for L in layers)
 
     def only(kind):
         for li, L in enumerate(layers):
@@ -329,27 +529,9 @@ def gpu_arm(args):
     per_kernel = []
     n_inst = max(5, min(args.steps, 20))
     for kind in range(0 if fused else 3):
-        gk = torch.cuda.CUDAGraph()
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            only(kind)
-            torch.cuda.synchronize()
-            with torch.cuda.graph(gk, stream=side):
-                only(kind)
-        torch.cuda.current_stream().wait_stream(side)
-        for _ in range(3):
-            gk.replay()
-        torch.cuda.synchronize()
-        k0, k1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        k0.record()
-        for _ in range(n_inst):
-            gk.replay()
-        k1e.record()
-        torch.cuda.synchronize()
-        per_kernel.append(k0.elapsed_time(k1e) / n_inst)    # ms per step spent in K1 / K2 / K3
+        per_kernel.append(time_graph(graph_of(lambda kind=kind: only(kind), dev), n_inst))   # ms per step in K1 / K2 / K3
 
-    # ---- e2e: host buffers through the C-ABI triple, H2D + D2H inside the timed region
+    # ---- e2e: host buffers through the C ABI, H2D + D2H inside the timed region
     h2d = sum(L["x_host"].numel() * 2 for L in layers)
     d2h = sum(L["y_host"].numel() * 2 for L in layers) + hist_host.numel() * 8
 
@@ -440,11 +622,6 @@ def gpu_arm(args):
     ms_total, ms_e2e = float(stats[0]), float(stats[1])
     ms_step = ms_total / args.steps
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
     peaks = {}
     peak_src = "fallback (B200_PROFILING.md)"
     try:
@@ -452,55 +629,79 @@ def gpu_arm(args):
         peak_src = "measured (MEASURED_PEAKS.json)"
     except (OSError, ValueError):
         peaks = {"bf16_tflops_sustained": 1400.0, "bf16_tflops": 1590.0, "hbm_gbs": 6650.0}
-    peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))   # kernel timed inside a long step
+    hbm_gbs = float(peaks.get("hbm_gbs", 6650.0))
+
+    # ---- the other two legs (every rank takes part: the sampling leg shards prompt batches and all-reduces)
+    sampling = None
+    if args.sampling_batches > 0:
+        sampling = sampling_leg(M, args, dev, rank, world, dist)
+    r_router = r_hist = None
+    if rank == 0 and not args.no_aux:
+        r_router, r_hist = aux_rooflines(M, args, dev, hbm_gbs, peak_src)
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    capped = bool(clocks and "sw_power_cap" in (clocks.get("reasons") or []))
+    peak_tf = float(peaks.get("bf16_tflops_sustained" if capped else "bf16_tflops", 1590.0))
+    peak_kind = "sustained (power cap seen in the sampled clocks)" if capped else "burst (no power cap in the sampled clocks)"
     if fused:
         # the step IS the dominant kernel: 16 launches of ffn_fused_kernel, nothing else in the timed region
         tf = (k1_flops + k3_flops) / (ms_step * 1e-3) / 1e12
+        tf_nec = (k1_flops + k3_necessary) / (ms_step * 1e-3) / 1e12
         roofline = dict(bound="tensor", kernel="ffn_fused_kernel (K1 + routing + K3 per layer)", achieved=round(tf, 2),
                         peak=peak_tf, unit="TFLOP/s", frac=round(tf / peak_tf, 4),
+                        achieved_necessary=round(tf_nec, 2), frac_necessary=round(tf_nec / peak_tf, 4),
                         # ncu --set full, dram__bytes_read + write of one launch (profiles/r01_ncu_full_fused_layer_d320.csv;
                         # d = 320, 8192 tokens: x 5.2 MB + weights 2.5 MB in, Y still in L2; H never leaves L2)
                         traffic=7.93e6, traffic_launch="ffn_fused_kernel d=320 T=8192", peak_source=peak_src,
+                        peak_kind=peak_kind,
                         algorithmic="6*d*h FLOP per token (4dh up-projection + 2dh dense-equivalent down-projection), "
                                     "summed over the step's 16 launches / the step time (CUDA events; the timed region "
-                                    "holds nothing but these launches)")
+                                    "holds nothing but these launches); *_necessary counts the down-projection at "
+                                    "2*d*es*k (active experts only)")
     else:
         k1_tf = k1_flops / (per_kernel[0] * 1e-3) / 1e12
         k3_tf = k3_flops / (per_kernel[2] * 1e-3) / 1e12
         roofline = dict(bound="tensor", kernel="geglu_up_kernel (K1)", achieved=round(k1_tf, 2), peak=peak_tf,
-                    unit="TFLOP/s", frac=round(k1_tf / peak_tf, 4),
-                    # ncu --set full, dram__bytes_read + write of the config-1 K1 launch (d=320, 8192 tokens; its
-                    # algorithmic bytes are 30 MB, of which the 21 MB H tile stays in L2): profiles/r01_ncu_full_v6_*
-                    traffic=6.93e6, traffic_launch="K1 d=320 T=8192", peak_source=peak_src,
-                    algorithmic="4*d*h FLOP per token, summed over the 16 K1 launches of a step / their summed "
-                                "duration (CUDA events around a graph of exactly those launches)",
-                    kernel_ms_per_step=dict(K1_geglu_up=round(per_kernel[0], 4), K2_router=round(per_kernel[1], 4),
-                                            K3_down_proj=round(per_kernel[2], 4)),
-                    K3_down_proj_tflops=round(k3_tf, 2), K3_frac=round(k3_tf / peak_tf, 4))
+                        unit="TFLOP/s", frac=round(k1_tf / peak_tf, 4),
+                        traffic=6.93e6, traffic_launch="K1 d=320 T=8192", peak_source=peak_src, peak_kind=peak_kind,
+                        algorithmic="4*d*h FLOP per token, summed over the 16 K1 launches of a step / their summed "
+                                    "duration (CUDA events around a graph of exactly those launches)",
+                        kernel_ms_per_step=dict(K1_geglu_up=round(per_kernel[0], 4), K2_router=round(per_kernel[1], 4),
+                                                K3_down_proj=round(per_kernel[2], 4)),
+                        K3_down_proj_tflops=round(k3_tf, 2), K3_frac=round(k3_tf / peak_tf, 4),
+                        K3_necessary_tflops=round(k3_necessary / (per_kernel[2] * 1e-3) / 1e12, 2))
 
     line = dict(metric="moe_ffn_tokens_per_s", value=world * tokens_per_step / (ms_step * 1e-3), unit="tokens/s",
                 n_gpus=world, steps=args.steps, warmup=max(3, args.warmup), ms_per_step=ms_step, higher_is_better=True,
                 scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
-                config=dict(workload="SD-1.5 MoEfied UNet, all 16 transformer-block FFNs, one denoising step, "
-                                     f"batch {B} (CFG), 64x64 latents (BASELINE configs[1])",
-                            experts=f"{args.experts}: expert_size {expert_size_for(args.experts, 1280)} @h=1280, "
-                                    f"top-k ratio {RATIO}",
-                            tokens_per_step_per_gpu=tokens_per_step, parallelism=f"prompt-sharded x{world}",
-                            l2="working set ~0.5 GB per step > 126 MB L2; no explicit flush",
-                            cuda_graph=graph is not None, path=args.path,
-                            counters="row-0 expert histogram fused in the routing stage"),
-                unet_steps_per_s=world * 1e3 / ms_step,
+                config=workload_config(args, world),
+                impl_details=dict(cuda_graph=graph is not None, path=args.path,
+                                  counters="row-0 expert histogram fused in the routing stage of the layer kernel"),
+                ffn_stack_steps_per_s=world * 1e3 / ms_step,
                 e2e=dict(value=world * tokens_per_step / (ms_e2e * 1e-3), unit="tokens/s", h2d_bytes_per_step=h2d,
                          d2h_bytes_per_step=d2h, ms_per_step=ms_e2e, cuda_graph=e2e_graph is not None,
                          copies_per_step=2 * len(groups) + 1, pipelined_steps=True, host_binding=numa,
+                         h2d_gbs_per_rank=round(h2d / (ms_e2e * 1e-3) / 1e9, 2),
+                         d2h_gbs_per_rank=round(d2h / (ms_e2e * 1e-3) / 1e9, 2),
                          output_abs_sum_layer0=y_check, outputs_equal_resident_run=e2e_same),
                 gpu_launches=launches_per_step * args.steps, clocks=clocks, roofline=roofline,
                 histogram_counts_exact=counts_ok)
+    if r_router is not None:
+        line["roofline_router"], line["roofline_hist"] = r_router, r_hist
+    if sampling is not None:
+        line["sampling"] = sampling
     if world == 1 and not args.no_cpu_baseline:
         cb, _ = cpu_arm(args, steps=2, warmup=1)
+        cb.pop("timed_region_s", None)
         line["cpu_baseline"] = cb
     print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -511,13 +712,15 @@ def main():
             return
         cb, tokens = cpu_arm(args, steps=args.steps, warmup=args.warmup)
         ms = cb.pop("ms_per_step")
+        wall = cb.pop("timed_region_s")
         line = dict(impl="reference", metric="moe_ffn_tokens_per_s", value=cb["value"], unit="tokens/s",
                     n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=ms, higher_is_better=True,
                     scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-                    config=dict(workload="SD-1.5 MoEfied UNet, all 16 transformer-block FFNs, one denoising step, "
-                                         f"batch {args.batch} (CFG), 64x64 latents (BASELINE configs[1])",
-                                experts=args.experts, note="reference's hook arithmetic on the host CPU (oracle port; "
-                                "the Python reference needs diffusers, absent from this image)"),
+                    config=workload_config(args, args.gpus),
+                    impl_details=dict(note="reference's hook arithmetic on the host CPU, all 16 layers every step (oracle "
+                                           "port, bit-identical to the reference classes on CPU; the Python reference needs "
+                                           "diffusers and /root/reference, absent from the GPU box)",
+                                      timed_region_s=round(wall, 3)),
                     cpu_baseline=dict(cb, value=cb["value"]),
                     e2e=dict(value=cb["value"], unit="tokens/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                     gpu_launches=0)

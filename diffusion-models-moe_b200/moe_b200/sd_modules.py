@@ -172,8 +172,73 @@ class SyntheticFFNPipeline:
         gen = torch.Generator(device="cpu").manual_seed(int(torch.initial_seed()) % (2 ** 31))
         states = [torch.randn(batch, s, d, generator=gen).to(self.device, self.dtype) for (_, d, _, s) in shapes]
         for _ in range(steps):
-            new = self.unet(states)
-            # keep the states O(1): the next step sees the re-normalised residual stream
-            states = [F.layer_norm(x.float(), x.shape[-1:]).to(self.dtype) for x in new]
+            # the residual stream of every block carries over to the next step (each block normalises its own
+            # FFN input with norm3, so the FFN sees O(1) activations at every step)
+            states = self.unet(states)
         per_prompt = [[x[2 * i:2 * i + 2] for x in states] for i in range(len(prompts))]
         return SyntheticFFNPipeline.Output(per_prompt)
+
+
+class GraphedSampling:
+    """One whole sampling run (`steps` UNet steps of the FFN stack for a batch of prompts) through a receiver's
+    hooks, captured ONCE as a CUDA graph and replayed per prompt batch -- the launch-bound Python hook path
+    (16 hooks x `steps` per prompt batch) runs only at capture time.
+
+    The receiver's (timestep, layer) state machine advances during capture, so every captured layer call is bound
+    to its own cell: the removed-expert bits of (t, l) and the histogram slice hist[t, l].  Replaying therefore
+    accumulates the per-timestep expert counters of every prompt batch into the receiver's device histogram
+    (reference flow: moefication/freq_expert_select.py:49-64, one `observe_activation` per prompt).
+
+        gs = GraphedSampling(pipe, receiver, n_prompts=8, steps=50)
+        gs.load_states(seed)     # this prompt batch's initial hidden states (any stream-ordered source)
+        gs.replay()              # enqueue the whole sampling run; gs.states_out holds the final states
+    """
+
+    def __init__(self, pipe, receiver, n_prompts: int, steps: int = None, warmup_steps: int = None):
+        self.pipe = pipe
+        self.receiver = receiver
+        self.steps = steps or pipe.num_inference_steps
+        self.batch = 2 * n_prompts                      # classifier-free guidance: 2 UNet rows per prompt
+        dev, dt = pipe.device, pipe.dtype
+        shapes = sd_ffn_shapes(pipe.unet.latent_hw)
+        self.states_in = [torch.zeros(self.batch, s, d, device=dev, dtype=dt) for (_, d, _, s) in shapes]
+        self.states_out = None
+        self.graph = None
+        self._capture(warmup_steps)
+
+    def load_states(self, seed: int):
+        """Seeded synthetic hidden states of one prompt batch (identical whichever rank draws them)."""
+        gen = torch.Generator(device=self.pipe.device).manual_seed(int(seed))
+        for x in self.states_in:
+            x.copy_(torch.randn(x.shape, generator=gen, device=x.device, dtype=torch.float32).to(x.dtype))
+
+    @torch.no_grad()
+    def _loop(self):
+        states = self.states_in
+        for _ in range(self.steps):
+            states = self.pipe.unet(states)      # same loop as SyntheticFFNPipeline.__call__
+        return states
+
+    @torch.no_grad()
+    def _capture(self, warmup_steps):
+        rec = self.receiver
+        hooks = rec.register_hooks(self.pipe)
+        try:
+            side = torch.cuda.Stream(device=self.pipe.device)
+            side.wait_stream(torch.cuda.current_stream(self.pipe.device))
+            with torch.cuda.stream(side):
+                # eager pass: kernel attributes, workspaces, and every per-(t, l) device artefact of the receiver
+                rec.reset_time_layer()
+                self._loop()
+                torch.cuda.synchronize()
+                rec.reset_time_layer()
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph, stream=side):
+                    self.states_out = self._loop()
+            torch.cuda.current_stream(self.pipe.device).wait_stream(side)
+        finally:
+            rec.remove_hooks(hooks)
+        rec.reset_time_layer()
+
+    def replay(self):
+        self.graph.replay()
