@@ -45,9 +45,18 @@ SIGNATURES = {
                               c_int, c_void_p, ctypes.c_size_t, c_void_p]),
     "moe_ffn_fused_workspace_bytes": (ctypes.c_size_t, [c_int, c_int, c_int]),
     "moe_debug_trace_fused": (c_int, [c_void_p, c_int]),
+    "moe_expert_permutation": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       ctypes.c_size_t, c_void_p]),
+    "moe_expert_permutation_workspace_bytes": (ctypes.c_size_t, [c_int, c_int]),
+    "moe_router_topk_perm": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, ctypes.c_size_t, c_void_p]),
+    "moe_down_grouped": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                 c_int, c_int, c_int, c_void_p, ctypes.c_size_t, c_void_p]),
+    "moe_down_grouped_rows": (ctypes.c_size_t, [c_int, c_int, c_int]),
+    "moe_down_grouped_workspace_bytes": (ctypes.c_size_t, [c_int, c_int, c_int, c_int]),
 }
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 _lib = None
 
 

@@ -88,7 +88,7 @@ int make_tmap_bf16_kblocks(CUtensorMap* out, const void* base, uint64_t rows, ui
 
 extern "C" {
 
-int moe_abi_version(void) { return 2; }
+int moe_abi_version(void) { return 3; }
 const char* moe_last_error(void) { return moe::last_error_buf(); }
 long long moe_launch_count(void) { return moe::g_launches.load(); }
 void moe_reset_launch_count(void) { moe::g_launches.store(0); }

@@ -46,6 +46,25 @@
 #ifndef MOE_TRACE
 #define MOE_TRACE 0
 #endif
+#define MOE_ROUTE_TRACE MOE_TRACE
+
+namespace moe {
+namespace fused {
+#if MOE_TRACE
+__device__ unsigned long long g_trace[256 * 64];
+#define TRACE(slot)                                                                                                                   \
+  do {                                                                                                                                \
+    if (blockIdx.x < 256 && (slot) < 64) ::moe::fused::g_trace[blockIdx.x * 64 + (slot)] = ::moe::tc::global_timer_ns();              \
+  } while (0)
+#else
+#define TRACE(slot) \
+  do {              \
+  } while (0)
+#endif
+}  // namespace fused
+}  // namespace moe
+
+#include "route.cuh"      // (after TRACE: the routing code carries timeline stamps in the trace build)
 
 namespace moe {
 namespace fused {
@@ -73,18 +92,6 @@ constexpr int kBlockRecInts = 32;
 constexpr int kMaxBlocks = 2048;                     // 128-row blocks (T <= 262144 tokens)
 constexpr size_t kSyncBytes = (kSyncHeaderInts + static_cast<size_t>(kMaxBlocks) * kBlockRecInts) * 4;
 constexpr size_t kSplitCounterBytes = 64 * 1024;
-
-#if MOE_TRACE
-__device__ unsigned long long g_trace[256 * 64];
-#define TRACE(slot)                                                                                       \
-  do {                                                                                                    \
-    if (blockIdx.x < 256 && (slot) < 64) g_trace[blockIdx.x * 64 + (slot)] = tc::global_timer_ns();       \
-  } while (0)
-#else
-#define TRACE(slot) \
-  do {              \
-  } while (0)
-#endif
 
 struct Barriers {   // the mbarriers first, in this order: the kernel initialises them by index
   uint64_t full[kMaxStages];
@@ -264,12 +271,6 @@ __device__ __forceinline__ uint64_t activate2(float x0, float x1) {
     return pk2(x0, x1);   // profiling only (trace build): no activation math
 }
 
-// order-preserving float -> uint32 key (ascending)
-__device__ __forceinline__ uint32_t float_key(float s) {
-  const uint32_t u = __float_as_uint(s);
-  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-
 // Every phase-3 item touches its block's record twice (its sync warp after the done-poll and its ready-add, its
 // A-tile producer after the ready-wait); the last of these 2 x consumers visits zeroes the record, so the sync area
 // is clean again when the kernel ends -- off the critical path, unlike a last-CTA-out sweep at kernel exit.
@@ -332,293 +333,8 @@ __device__ __forceinline__ bool item3(const Shape& g, int it, int p, int P, int 
   return true;
 }
 
-// ------------------------------------------------------------------------------------------ routing
-// One chunk = 32 consecutive tokens of one 128-row block; 16 lanes own one token (2 tokens per warp), each lane
-// KPT consecutive experts.  Exact k-th largest score by bisection on the order-preserving integer keys (MSB first,
-// starting below the key prefix the whole warp shares, stopping as soon as both tokens of the warp have separated
-// exactly k keys); ties on the k-th key go to the lowest expert ids.  Outputs: expert-set words (what the
-// down-projection masks with), ascending labels, histogram (shared-memory bins) and, only when the caller wants
-// the masked hidden state materialised, write-only zeroing of H (16-byte stores, a whole warp per token row).
-template <int KPT>
-__device__ __forceinline__ void route_chunk(const Shape& g, const Ptrs& a, int tok0, int tok_end, int ew, int lane,
-                                            uint32_t* s_words, unsigned int* s_hist) {
-  const unsigned full = 0xffffffffu;
-  const int L = g.lanes;
-  const int tpw = 32 >> g.lanes_log2;           // tokens per warp
-  const int part = lane & (L - 1);
-  const int tl = lane >> g.lanes_log2;
-  // per-token sums over the token's L lanes with full-warp REDUX instructions: every token of the warp owns a
-  // bit field of the reduced word (16 bits for 2 tokens per warp, 8 bits for 4 or 8 tokens -- 8 tokens take two
-  // reductions); a field never overflows because a token has at most E <= 16 L experts.  (A reduction over a
-  // per-token member mask compiles to a divergent slow path: ~550 cycles per bisection round.)
-  const int fshift = (tpw <= 2) ? 16 * tl : 8 * (tl & 3);
-  const uint32_t fmask = (tpw == 1) ? 0xffffffffu : (tpw == 2) ? 0xffffu : 0xffu;
-  auto token_sum = [&](int c) -> int {
-    const uint32_t v = static_cast<uint32_t>(c) << fshift;
-    uint32_t r;
-    if (tpw == 8) {
-      const uint32_t r0 = __reduce_add_sync(full, tl < 4 ? v : 0u);
-      const uint32_t r1 = __reduce_add_sync(full, tl < 4 ? 0u : v);
-      r = tl < 4 ? r0 : r1;
-    } else {
-      r = __reduce_add_sync(full, v);
-    }
-    return static_cast<int>((r >> fshift) & fmask);
-  };
-  const int t = tok0 + tpw * ew + tl;
-  const bool t_ok = t < tok_end;   // tok_end <= T: end of the 128-row block (a chunk never leaves its block)
-  const int e0 = part * KPT;
-  const int E = g.E;
-
-  uint32_t key[KPT];
-  uint32_t valid = 0u, removed = 0u;
-  if (a.removed_bits != nullptr && e0 < E) removed = (__ldg(a.removed_bits + (e0 >> 5)) >> (e0 & 31)) & ((KPT == 32) ? ~0u : ((1u << KPT) - 1u));
-  {
-    const float* row = a.scores + static_cast<size_t>(t_ok ? t : 0) * E + e0;
-    if constexpr (KPT % 4 == 0) {
-      if ((E & 3) == 0) {
-#pragma unroll
-        for (int i4 = 0; i4 < KPT / 4; ++i4) {
-          float4 sc = make_float4(0.f, 0.f, 0.f, 0.f);
-          const bool in = t_ok && (e0 + 4 * i4) < E;
-          if (in) {
-            sc = __ldcg(reinterpret_cast<const float4*>(row + 4 * i4));
-            valid |= 0xfu << (4 * i4);
-          }
-          const float sv[4] = {sc.x, sc.y, sc.z, sc.w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int i = 4 * i4 + j;
-            const float v = ((removed >> i) & 1u) ? 0.f : sv[j];   // zeroed pattern row => score exactly 0
-            key[i] = in ? float_key(v) : 0u;
-          }
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < KPT; ++i) {
-          const bool in = t_ok && (e0 + i) < E;
-          float v = in ? __ldcg(row + i) : 0.f;
-          if ((removed >> i) & 1u) v = 0.f;
-          key[i] = in ? float_key(v) : 0u;
-          if (in) valid |= 1u << i;
-        }
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < KPT; ++i) {
-        const bool in = t_ok && (e0 + i) < E;
-        float v = in ? __ldcg(row + i) : 0.f;
-        if ((removed >> i) & 1u) v = 0.f;
-        key[i] = in ? float_key(v) : 0u;
-        if (in) valid |= 1u << i;
-      }
-    }
-  }
-#if MOE_TRACE
-  if (ew == 0 && lane == 0) TRACE(56);
-#endif
-
-  uint32_t sel = 0u;   // KPT-bit mask over this lane's experts
-  if (g.k >= E) {
-    sel = valid;
-  } else if (g.k > 0) {
-    uint32_t prefix;
-    if (L == 32) {
-      // a whole warp per token: MSB-first bisection on the keys, one full-mask REDUX per round (~60 cycles of
-      // dependent latency per round, ~20 rounds) -- a single warp walks the 36-stage sorting network of 256 keys in
-      // ~4000 cycles, three times as long
-      uint32_t k_or = 0u, k_and = full;
-#pragma unroll
-      for (int i = 0; i < KPT; ++i)
-        if ((valid >> i) & 1u) {
-          k_or |= key[i];
-          k_and &= key[i];
-        }
-      k_or = __reduce_or_sync(full, k_or);
-      k_and = __reduce_and_sync(full, k_and);
-      const uint32_t diff = k_or ^ k_and;
-      prefix = k_and;                       // every valid key identical
-      if (diff != 0u && t_ok) {
-        const int top = 31 - __clz(diff);
-        prefix = (top == 31) ? 0u : (k_and & ~((2u << top) - 1u));
-        for (int bit = top; bit >= 0; --bit) {
-          const uint32_t thr = prefix | (1u << bit);
-          int c = 0;
-#pragma unroll
-          for (int i = 0; i < KPT; ++i) c += (key[i] >= thr) ? 1 : 0;
-          c = __reduce_add_sync(full, c);
-          if (c >= g.k) prefix = thr;
-          if (c == g.k) break;              // exactly k keys at or above the threshold: done (warp-uniform)
-        }
-      }
-    } else {
-    // k-th largest key of the token: bitonic sort of its N = KPT * L keys (element i = part * KPT + r; invalid
-    // slots hold key 0 and sink to the bottom), compare-exchanges inside a lane for distances < KPT and through
-    // shuffles beyond.  ~250 instructions and ~700 cycles per pass regardless of the data; the MSB-first bisection
-    // this replaces needed ~20 dependent REDUX + VOTE rounds (3-6 us per pass).
-    uint32_t srt[KPT];
-#pragma unroll
-    for (int r = 0; r < KPT; ++r) srt[r] = key[r];
-    // sizes up to KPT: entirely inside the lane, directions known at compile time except for size == KPT ... N
-#pragma unroll
-    for (int size = 2; size <= KPT; size <<= 1) {
-      const bool lane_up = ((part * KPT) & size) == 0;   // only matters for size == KPT's parent bit: (i & size)
-#pragma unroll
-      for (int stride = size >> 1; stride >= 1; stride >>= 1) {
-#pragma unroll
-        for (int r = 0; r < KPT; ++r) {
-          if ((r & stride) == 0) {
-            const bool up = (size < KPT) ? ((r & size) == 0) : lane_up;
-            const uint32_t lo = min(srt[r], srt[r | stride]), hi = max(srt[r], srt[r | stride]);
-            srt[r] = up ? lo : hi;
-            srt[r | stride] = up ? hi : lo;
-          }
-        }
-      }
-    }
-    // sizes beyond one lane: lane distances L' = size / KPT / 2 ... 1 through shuffles, then the in-lane strides
-    for (int lsize = 2; lsize <= L; lsize <<= 1) {        // size = lsize * KPT
-      const bool up = (part & lsize) == 0 || lsize == L;   // the last merge sorts everything ascending
-      for (int ls = lsize >> 1; ls >= 1; ls >>= 1) {
-        const bool lower = (part & ls) == 0;
-        const bool keep_min = lower == up;
-#pragma unroll
-        for (int r = 0; r < KPT; ++r) {
-          const uint32_t other = __shfl_xor_sync(full, srt[r], ls);
-          srt[r] = keep_min ? min(srt[r], other) : max(srt[r], other);
-        }
-      }
-#pragma unroll
-      for (int stride = KPT >> 1; stride >= 1; stride >>= 1) {
-#pragma unroll
-        for (int r = 0; r < KPT; ++r) {
-          if ((r & stride) == 0) {
-            const uint32_t lo = min(srt[r], srt[r | stride]), hi = max(srt[r], srt[r | stride]);
-            srt[r] = up ? lo : hi;
-            srt[r | stride] = up ? hi : lo;
-          }
-        }
-      }
-    }
-    // ascending over the token's lanes: the k-th largest sits at element N - k
-    const int pos = KPT * L - g.k;
-    uint32_t mine = 0u;
-#pragma unroll
-    for (int r = 0; r < KPT; ++r) mine = (r == (pos & (KPT - 1))) ? srt[r] : mine;
-    prefix = __shfl_sync(full, mine, (lane & ~(L - 1)) + pos / KPT);
-    }
-    // keys above the k-th value, then ties on it from the lowest expert id
-    uint32_t gt = 0u, eq = 0u;
-#pragma unroll
-    for (int i = 0; i < KPT; ++i) {
-      const bool v = (valid >> i) & 1u;
-      gt |= (v && key[i] > prefix) ? (1u << i) : 0u;
-      eq |= (v && key[i] == prefix) ? (1u << i) : 0u;
-    }
-    const int n_gt = token_sum(__popc(gt));
-    const int n_eq = __popc(eq);
-    int incl = n_eq;
-    for (int o = 1; o < L; o <<= 1) {
-      const int v = __shfl_up_sync(full, incl, o, L);
-      if (part >= o) incl += v;
-    }
-    int take = g.k - n_gt - (incl - n_eq);
-    take = take < 0 ? 0 : (take > n_eq ? n_eq : take);
-    uint32_t ties = 0u, w = eq;
-    for (int j = 0; j < take; ++j) {
-      const uint32_t low = w & (0u - w);
-      ties |= low;
-      w ^= low;
-    }
-    sel = gt | ties;
-  }
-#if MOE_TRACE
-  if (ew == 0 && lane == 0) TRACE(57);
-#endif
-
-  // expert-set words: OR the lanes' masks of each 32-expert word together (butterfly inside the word's lanes)
-  const uint32_t active = sel & ~removed;
-  const int lanes_per_word = (32 / KPT) < L ? (32 / KPT) : L;
-  uint32_t word = active << ((part * KPT) & 31);
-  for (int o = 1; o < lanes_per_word; o <<= 1) word |= __shfl_xor_sync(full, word, o);
-  const int widx = (part * KPT) >> 5;
-  if ((part & (lanes_per_word - 1)) == 0 && widx < g.words) {
-    s_words[tl * g.words + widx] = word;
-    if (t_ok && a.active_bits != nullptr) a.active_bits[static_cast<size_t>(t) * g.words + widx] = word;
-  }
-
-  if (a.idx != nullptr) {
-    const int n_sel = __popc(sel);
-    int incl = n_sel;
-    for (int o = 1; o < L; o <<= 1) {
-      const int v = __shfl_up_sync(full, incl, o, L);
-      if (part >= o) incl += v;
-    }
-    if (t_ok) {
-      int16_t* out = a.idx + static_cast<size_t>(t) * g.k + (incl - n_sel);
-      uint32_t w = sel;
-      while (w) {
-        const int i = __ffs(w) - 1;
-        *out++ = static_cast<int16_t>(e0 + i);
-        w &= w - 1;
-      }
-    }
-  }
-
-  if (a.hist != nullptr && t_ok && t >= g.count_begin && t < g.count_end) {
-    uint32_t w = sel;
-    while (w) {
-      const int i = __ffs(w) - 1;
-      atomicAdd(&s_hist[e0 + i], 1u);
-      w &= w - 1;
-    }
-  }
-  __syncwarp();
-#if MOE_TRACE
-  if (ew == 0 && lane == 0) TRACE(58);
-#endif
-
-  if (g.mask_h && (g.k < E || a.removed_bits != nullptr)) {   // k == E still masks the removed experts' neurons
-    // materialise the masked hidden state: zero the neurons of every expert outside the token's active set
-    // (write-only; 16-byte units, 4-neuron groups never straddle an expert because es % 4 == 0)
-    const int units = g.h >> 3;
-    for (int tt = 0; tt < tpw; ++tt) {
-      const int tok = tok0 + tpw * ew + tt;
-      if (tok >= tok_end) break;
-      const uint32_t* wtok = s_words + tt * g.words;
-      uint4* hrow = reinterpret_cast<uint4*>(a.H + static_cast<size_t>(tok) * g.h);
-      // two predicated 8-byte stores per 16-byte unit and no branches: a three-way if / else (16-byte store, or
-      // either half) made the warp run each store flavour in turn
-#pragma unroll 4
-      for (int u = lane; u < units; u += 32) {
-        const uint32_t ea = __umulhi(static_cast<uint32_t>(u) << 3, g.es_magic);
-        const uint32_t eb = __umulhi((static_cast<uint32_t>(u) << 3) + 4u, g.es_magic);
-        const bool on_a = (wtok[ea >> 5] >> (ea & 31u)) & 1u;
-        const bool on_b = (wtok[eb >> 5] >> (eb & 31u)) & 1u;
-        uint2* half = reinterpret_cast<uint2*>(hrow + u);
-        if (!on_a) half[0] = make_uint2(0u, 0u);
-        if (!on_b) half[1] = make_uint2(0u, 0u);
-      }
-    }
-  }
-  __syncwarp();
-#if MOE_TRACE
-  if (ew == 0 && lane == 0) TRACE(59);
-#endif
-}
-
-__device__ __forceinline__ void route_dispatch(const Shape& g, const Ptrs& a, int tok0, int tok_end, int ew, int lane,
-                                               uint32_t* s_words, unsigned int* s_hist) {
-  if (ew >= g.route_warps) return;   // small chunks (many consumers per block) use only the first warps
-  switch (g.kpt) {
-    case 16: route_chunk<16>(g, a, tok0, tok_end, ew, lane, s_words, s_hist); break;
-    case 8: route_chunk<8>(g, a, tok0, tok_end, ew, lane, s_words, s_hist); break;
-    case 4: route_chunk<4>(g, a, tok0, tok_end, ew, lane, s_words, s_hist); break;
-    case 2: route_chunk<2>(g, a, tok0, tok_end, ew, lane, s_words, s_hist); break;
-    case 1: route_chunk<1>(g, a, tok0, tok_end, ew, lane, s_words, s_hist); break;
-    default: break;
-  }
-}
+using route::route_chunk;
+using route::route_dispatch;
 
 // ------------------------------------------------------------------------------------------ the kernel
 // per-warp bias slices staged in shared memory: lanes load coalesced, everyone re-reads float4 broadcasts

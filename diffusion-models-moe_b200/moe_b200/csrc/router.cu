@@ -2,6 +2,7 @@
 // standalone K4 histogram / column-max kernels.  HBM/L2-bound integer & compare work: one warp
 // per token, everything warp-uniform after the ballots, no shared-memory traffic in the select.
 #include "common.cuh"
+#include "route.cuh"
 
 namespace moe {
 
@@ -225,48 +226,274 @@ __global__ void __launch_bounds__(kRouterWarps * 32) router_topk_kernel(const Ro
   }
 }
 
-// ------------------------------------------------------------------ K4 standalone histogram
-__device__ __forceinline__ void hist_add_aggregated(unsigned int* bins, int v, int E, int lane) {
-  const bool ok = v >= 0 && v < E;
-  const unsigned peers = __match_any_sync(0xffffffffu, ok ? v : -1);
-  if (ok && lane == (__ffs(peers) - 1)) atomicAdd(&bins[v], static_cast<unsigned int>(__popc(peers)));
+// ------------------------------------------------------------------ K2, several tokens per warp (E <= 256)
+// The warp-per-token kernel above spends ~700 warp instructions per token (about 20 dependent ballot rounds): at the
+// UNet-batch-16 shapes it runs at 1.3 G tokens/s = 8 % of the HBM rate of its 4E-byte score rows.  This kernel routes
+// with the code of the fused layer kernel's routing stage (route.cuh): L = 4 / 8 / 16 lanes per token (8 / 4 / 2
+// tokens per warp, <= 16 experts per lane in registers), the k-th largest key from a bitonic sort -- ~60-90 warp
+// instructions per token -- 16-byte score loads, shared-memory histogram bins, whole-warp 16-byte zero stores.
+struct RouterGeom {
+  int lanes, lanes_log2, E, k, words, mask_h, h, count_begin, count_end, T, chunk_tokens;
+  uint32_t es_magic;
+};
+struct RouterPtrs {
+  const float* scores;
+  const float* score_bias;
+  const uint32_t* removed_bits;
+  uint32_t* active_bits;
+  int16_t* idx;
+  unsigned long long* hist;
+  float* colmax;
+  __nv_bfloat16* H;
+};
+
+constexpr int kMultiWarps = 8;
+
+template <int KPT, bool kBias, bool kColmax>
+__global__ void __launch_bounds__(kMultiWarps * 32) router_multi_kernel(const RouterGeom g, const RouterPtrs a) {
+  __shared__ uint32_t s_words[kMultiWarps][16];
+  __shared__ unsigned int s_hist[256];
+  __shared__ float s_max[kColmax ? kMultiWarps * 32 * KPT : 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0u;
+  __syncthreads();
+  pdl_wait();                 // scores / H come from the previous kernel in the stream
+  pdl_launch_dependents();
+  float mx[KPT];
+#pragma unroll
+  for (int i = 0; i < KPT; ++i) mx[i] = -INFINITY;
+  const long long n_chunks = (static_cast<long long>(g.T) + g.chunk_tokens - 1) / g.chunk_tokens;
+  for (long long c = blockIdx.x; c < n_chunks; c += gridDim.x)
+    route::route_chunk<KPT, kBias, kColmax>(g, a, static_cast<int>(c * g.chunk_tokens), g.T, warp, lane, s_words[warp],
+                                            s_hist, mx);
+  __syncthreads();
+  if (a.hist != nullptr)
+    for (int i = threadIdx.x; i < g.E; i += blockDim.x)
+      if (s_hist[i]) atomicAdd(a.hist + i, static_cast<unsigned long long>(s_hist[i]));
+  if constexpr (kColmax) {
+    // lane `part` of every token group holds experts [part * KPT, part * KPT + KPT)
+#pragma unroll
+    for (int i = 0; i < KPT; ++i) s_max[(warp * 32 + lane) * KPT + i] = mx[i];
+    __syncthreads();
+    const int L = g.lanes;
+    for (int e = threadIdx.x; e < g.E; e += blockDim.x) {
+      const int part = e / KPT, i = e - part * KPT;
+      float m = -INFINITY;
+      for (int w = 0; w < kMultiWarps; ++w)
+        for (int tl = 0; tl < 32 / L; ++tl) m = fmaxf(m, s_max[(w * 32 + tl * L + part) * KPT + i]);
+      if (m > -INFINITY) atomic_max_float(a.colmax + e, m);
+    }
+  }
 }
 
-__global__ void __launch_bounds__(256) hist_accumulate_kernel(const int16_t* __restrict__ idx, long long n, int E,
-                                                              unsigned long long* __restrict__ hist) {
-  extern __shared__ unsigned int bins[];
-  for (int i = threadIdx.x; i < E; i += blockDim.x) bins[i] = 0u;
+template <int KPT>
+static cudaError_t launch_multi(const RouterGeom& g, const RouterPtrs& a, int grid, cudaStream_t st) {
+  const bool bias = a.score_bias != nullptr, cmax = a.colmax != nullptr;
+  if (bias && cmax) return launch_pdl(router_multi_kernel<KPT, true, true>, dim3(grid), dim3(kMultiWarps * 32), 0, st, g, a);
+  if (bias) return launch_pdl(router_multi_kernel<KPT, true, false>, dim3(grid), dim3(kMultiWarps * 32), 0, st, g, a);
+  if (cmax) return launch_pdl(router_multi_kernel<KPT, false, true>, dim3(grid), dim3(kMultiWarps * 32), 0, st, g, a);
+  return launch_pdl(router_multi_kernel<KPT, false, false>, dim3(grid), dim3(kMultiWarps * 32), 0, st, g, a);
+}
+
+// ------------------------------------------------------------------ compacted token -> expert permutation
+// From the expert-set words of the router: for every expert e the ascending list of the tokens that selected it,
+// perm_tokens[perm_offsets[e] ... + perm_counts[e]), segments padded to a multiple of `row_pad` rows (pad entries -1),
+// and the inverse map slot_pos[t * k + j] = position of token t's j-th active expert (ascending expert id; -1 beyond
+// the token's active count).  Deterministic: a stable counting sort -- per (word, token segment, warp) counts, then an
+// ordered scatter -- no atomics.  Grid (words, segments); warp q of a CTA owns a contiguous token sub-range.
+constexpr int kPermWarps = 8;
+constexpr int kPermMaxSegments = 16;
+
+struct PermArgs {
+  const uint32_t* bits;   // [T, W]
+  int T, E, W, k, row_pad, seg_tokens, n_segments;
+  int* seg_counts;        // [W * 32][n_segments]
+  int* offsets;           // [E + 1]
+  int* counts;            // [E]
+  int* tokens;            // [capacity]
+  int* slot_pos;          // [T, k]
+};
+
+// per-warp counts of one token sub-range: lane b ends up with the number of tokens whose word has bit b set
+__device__ __forceinline__ int perm_count_range(const PermArgs& p, int w, int t0, int t1, int lane) {
+  int cnt = 0;
+  for (int base = t0; base < t1; base += 32) {
+    const int t = base + lane;
+    const uint32_t word = (t < t1) ? __ldg(p.bits + static_cast<size_t>(t) * p.W + w) : 0u;
+#pragma unroll
+    for (int b = 0; b < 32; ++b) {
+      const unsigned m = __ballot_sync(0xffffffffu, (word >> b) & 1u);
+      if (lane == b) cnt += __popc(m);
+    }
+  }
+  return cnt;
+}
+
+__device__ __forceinline__ void perm_warp_range(const PermArgs& p, int seg, int warp, int& t0, int& t1) {
+  const int s0 = seg * p.seg_tokens;
+  const int s1 = min(p.T, s0 + p.seg_tokens);
+  const int per = ((p.seg_tokens / kPermWarps) + 31) / 32 * 32;
+  t0 = min(s1, s0 + warp * per);
+  t1 = (warp == kPermWarps - 1) ? s1 : min(s1, t0 + per);
+}
+
+__global__ void __launch_bounds__(kPermWarps * 32) perm_count_kernel(const PermArgs p) {
+  __shared__ int s_cnt[kPermWarps][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int w = blockIdx.x, seg = blockIdx.y;
+  pdl_wait();
+  pdl_launch_dependents();
+  int t0, t1;
+  perm_warp_range(p, seg, warp, t0, t1);
+  s_cnt[warp][lane] = perm_count_range(p, w, t0, t1, lane);
+  __syncthreads();
+  if (warp == 0) {
+    int tot = 0;
+#pragma unroll
+    for (int q = 0; q < kPermWarps; ++q) tot += s_cnt[q][lane];
+    p.seg_counts[(w * 32 + lane) * p.n_segments + seg] = tot;
+  }
+}
+
+__global__ void __launch_bounds__(kPermWarps * 32) perm_scatter_kernel(const PermArgs p) {
+  __shared__ int s_cnt[kPermWarps][32];
+  __shared__ int s_base[32];       // first position of this CTA's segment for each of the word's experts
+  __shared__ int s_total[32], s_off[33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int w = blockIdx.x, seg = blockIdx.y;
+  pdl_wait();
+  pdl_launch_dependents();
+  int t0, t1;
+  perm_warp_range(p, seg, warp, t0, t1);
+  s_cnt[warp][lane] = perm_count_range(p, w, t0, t1, lane);
+  // padded offsets of this word's experts: sum over all experts below (every CTA redoes the small scan)
+  if (warp == 0) {
+    int before = 0;      // padded rows of all experts of lower words
+    for (int e = lane; e < w * 32; e += 32) {
+      int c = 0;
+      for (int s2 = 0; s2 < p.n_segments; ++s2) c += __ldg(p.seg_counts + e * p.n_segments + s2);
+      before += (c + p.row_pad - 1) / p.row_pad * p.row_pad;
+    }
+    for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+    int mine = 0, below_seg = 0;
+    const int e = w * 32 + lane;
+    if (e < p.E)
+      for (int s2 = 0; s2 < p.n_segments; ++s2) {
+        const int c = __ldg(p.seg_counts + e * p.n_segments + s2);
+        mine += c;
+        if (s2 < seg) below_seg += c;
+      }
+    const int padded = (mine + p.row_pad - 1) / p.row_pad * p.row_pad;
+    int incl = padded;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const int off = before + incl - padded;
+    s_off[lane] = off;
+    if (lane == 31) s_off[32] = before + incl;
+    s_total[lane] = mine;
+    s_base[lane] = off + below_seg;
+    if (seg == 0 && e < p.E) {
+      p.offsets[e] = off;
+      p.counts[e] = mine;
+      if (e == p.E - 1) p.offsets[p.E] = off + padded;
+    }
+  }
+  __syncthreads();
+  // this warp's first position per expert: segment base + the counts of the warps before it
+  int run = s_base[lane];
+  for (int q = 0; q < warp; ++q) run += s_cnt[q][lane];
+  const uint32_t lt = (1u << lane) - 1u;
+  for (int base = t0; base < t1; base += 32) {
+    const int t = base + lane;
+    const bool ok = t < t1;
+    const uint32_t word = ok ? __ldg(p.bits + static_cast<size_t>(t) * p.W + w) : 0u;
+    int j0 = 0;          // active experts of this token in lower words
+    if (ok)
+      for (int w2 = 0; w2 < w; ++w2) j0 += __popc(__ldg(p.bits + static_cast<size_t>(t) * p.W + w2));
+#pragma unroll
+    for (int b = 0; b < 32; ++b) {
+      const unsigned m = __ballot_sync(0xffffffffu, (word >> b) & 1u);
+      const int start = __shfl_sync(0xffffffffu, run, b);
+      if ((word >> b) & 1u) {
+        const int pos = start + __popc(m & lt);
+        p.tokens[pos] = t;
+        const int j = j0 + __popc(word & ((1u << b) - 1u));
+        if (j < p.k) p.slot_pos[static_cast<size_t>(t) * p.k + j] = pos;
+      }
+      if (lane == b) run += __popc(m);
+    }
+    if (ok && w == p.W - 1)
+      for (int j = j0 + __popc(word); j < p.k; ++j) p.slot_pos[static_cast<size_t>(t) * p.k + j] = -1;
+  }
+  // the last segment's CTA pads the tail of each of its experts' lists
+  if (seg == p.n_segments - 1) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32 * p.row_pad; i += blockDim.x) {
+      const int e_l = i / p.row_pad, r = i - e_l * p.row_pad;
+      if (w * 32 + e_l >= p.E) break;
+      const int begin = s_off[e_l] + s_total[e_l] + r;
+      if (begin < s_off[e_l + 1]) p.tokens[begin] = -1;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ K4 standalone histogram
+// 16-byte loads (8 labels), per-warp private shared-memory bins updated with native shared atomics (no return value:
+// RED.shared), folded and flushed with one int64 global atomic per expert per CTA.  (The round-1 kernel aggregated
+// equal labels with __match_any_sync first: ~16 match instructions per 16 bytes, 159 GB/s = 2 % of HBM.)
+constexpr int kHistWarps = 8;
+
+__global__ void __launch_bounds__(kHistWarps * 32) hist_accumulate_kernel(const int16_t* __restrict__ idx, long long n, int E,
+                                                                          int copies, unsigned long long* __restrict__ hist) {
+  extern __shared__ unsigned int bins[];      // [copies][E]: warp q updates copy q % copies
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < copies * E; i += blockDim.x) bins[i] = 0u;
   __syncthreads();
   pdl_wait();
   pdl_launch_dependents();
-  const int lane = threadIdx.x & 31;
+  unsigned int* mine = bins + (warp % copies) * E;
   const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
   const bool aligned = (reinterpret_cast<uintptr_t>(idx) & 15) == 0;
   const long long nvec = aligned ? (n >> 3) : 0;  // 8 labels per 16-byte load
   const int4* v4 = reinterpret_cast<const int4*>(idx);
-  // full-warp trips so that __match_any_sync always sees 32 lanes
-  const long long vec_trips = (nvec + nthreads - 1) / nthreads;
-  for (long long it = 0; it < vec_trips; ++it) {
-    const long long i = it * nthreads + tid;
-    int4 q = make_int4(-1, -1, -1, -1);
-    if (i < nvec) q = __ldg(v4 + i);
-    const int w[4] = {q.x, q.y, q.z, q.w};
+  auto add = [&](int v) {
+    if (v >= 0 && v < E) atomicAdd(mine + v, 1u);
+  };
+  long long i = tid;
+  for (; i + 3 * nthreads < nvec; i += 4 * nthreads) {     // four loads in flight per thread
+    int4 q[4];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      hist_add_aggregated(bins, static_cast<int16_t>(w[c] & 0xffff), E, lane);
-      hist_add_aggregated(bins, static_cast<int16_t>((w[c] >> 16) & 0xffff), E, lane);
+    for (int u = 0; u < 4; ++u) q[u] = __ldg(v4 + i + u * nthreads);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int wv[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        add(static_cast<int16_t>(wv[c] & 0xffff));
+        add(static_cast<int16_t>((wv[c] >> 16) & 0xffff));
+      }
     }
   }
-  const long long tail0 = nvec << 3;
-  const long long tail_trips = (n - tail0 + nthreads - 1) / nthreads;
-  for (long long it = 0; it < tail_trips; ++it) {
-    const long long i = tail0 + it * nthreads + tid;
-    hist_add_aggregated(bins, i < n ? static_cast<int>(idx[i]) : -1, E, lane);
+  for (; i < nvec; i += nthreads) {
+    const int4 q = __ldg(v4 + i);
+    const int wv[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      add(static_cast<int16_t>(wv[c] & 0xffff));
+      add(static_cast<int16_t>((wv[c] >> 16) & 0xffff));
+    }
   }
+  for (long long j = (nvec << 3) + tid; j < n; j += nthreads) add(static_cast<int>(idx[j]));
+  (void)lane;
   __syncthreads();
-  for (int i = threadIdx.x; i < E; i += blockDim.x)
-    if (bins[i]) atomicAdd(hist + i, static_cast<unsigned long long>(bins[i]));
+  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+    unsigned int tot = 0;
+    for (int w = 0; w < copies; ++w) tot += bins[w * E + e];
+    if (tot) atomicAdd(hist + e, static_cast<unsigned long long>(tot));
+  }
 }
 
 // ------------------------------------------------------------------ column max over tokens
@@ -342,12 +569,48 @@ int moe_router_topk_biased(const float* scores, const float* score_bias, const u
   a.count_begin = count_begin;
   a.count_end = count_end;
   a.es_magic = es >= 1 ? static_cast<uint32_t>((0x100000000ull / static_cast<unsigned>(es)) + 1ull) : 0u;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t le = cudaSuccess;
+  const char* legacy_env = getenv("MOE_ROUTER_LEGACY");       // tests / A-B timing: force the warp-per-token kernel
+  const bool legacy = legacy_env != nullptr && atoi(legacy_env) != 0;
+  const bool vec_ok = H == nullptr || (es % 4 == 0 && h % 8 == 0 && (reinterpret_cast<uintptr_t>(H) & 15) == 0);
+  if (E <= 256 && vec_ok && !legacy) {
+    // several tokens per warp (route.cuh): the smallest lane count per token that keeps <= 16 experts per lane
+    RouterGeom g = {};
+    int L = 4;
+    while (L < 32 && (E + L - 1) / L > 16) L <<= 1;
+    int kpt = 1;
+    while (kpt * L < E) kpt <<= 1;
+    g.lanes = L;
+    g.lanes_log2 = L == 4 ? 2 : (L == 8 ? 3 : (L == 16 ? 4 : 5));
+    g.E = E;
+    g.k = k;
+    g.words = (E + 31) / 32;
+    g.mask_h = H != nullptr ? 1 : 0;
+    g.h = h;
+    g.count_begin = count_begin;
+    g.count_end = count_end;
+    g.T = T;
+    g.chunk_tokens = kMultiWarps * (32 / L);
+    g.es_magic = a.es_magic;
+    RouterPtrs rp = {scores, score_bias, removed_bits, active_bits, idx, hist, score_colmax, static_cast<__nv_bfloat16*>(H)};
+    const long long chunks = (static_cast<long long>(T) + g.chunk_tokens - 1) / g.chunk_tokens;
+    const long long cap = static_cast<long long>(sm_count()) * 6;
+    const int grid = static_cast<int>(chunks < cap ? chunks : cap);
+    switch (kpt) {
+      case 16: le = launch_multi<16>(g, rp, grid, st); break;
+      case 8: le = launch_multi<8>(g, rp, grid, st); break;
+      case 4: le = launch_multi<4>(g, rp, grid, st); break;
+      case 2: le = launch_multi<2>(g, rp, grid, st); break;
+      default: le = launch_multi<1>(g, rp, grid, st); break;
+    }
+    if (le != cudaSuccess) return fail(MOE_ERR_CUDA, "moe_router_topk launch: %s", cudaGetErrorString(le));
+    return check_launch("moe_router_topk");
+  }
   const int ctas_needed = (T + kRouterWarps - 1) / kRouterWarps;
   const int max_ctas = sm_count() * 8;  // 8 resident CTAs of 256 threads per SM
   const int grid = ctas_needed < max_ctas ? ctas_needed : max_ctas;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int slots = (E + 31) / 32;
-  cudaError_t le = cudaSuccess;
   if (slots <= 1)
     le = launch_pdl(router_topk_kernel<1>, dim3(grid), dim3(kRouterWarps * 32), 0, st, a);
   else if (slots <= 2)
@@ -373,10 +636,73 @@ int moe_hist_accumulate(const int16_t* idx, long long n, int E, unsigned long lo
   long long ctas = (n + per_cta - 1) / per_cta;
   const long long max_ctas = static_cast<long long>(sm_count()) * 8;
   if (ctas > max_ctas) ctas = max_ctas;
-  cudaError_t le = launch_pdl(hist_accumulate_kernel, dim3(static_cast<unsigned>(ctas)), dim3(256), E * sizeof(unsigned int),
-                              static_cast<cudaStream_t>(stream), idx, n, E, hist);
+  const int copies = E <= 1024 ? kHistWarps : 1;       // private bins per warp while they fit 32 KB
+  cudaError_t le = launch_pdl(hist_accumulate_kernel, dim3(static_cast<unsigned>(ctas)), dim3(kHistWarps * 32),
+                              static_cast<size_t>(copies) * E * sizeof(unsigned int), static_cast<cudaStream_t>(stream), idx, n, E,
+                              copies, hist);
   if (le != cudaSuccess) return fail(MOE_ERR_CUDA, "moe_hist_accumulate launch: %s", cudaGetErrorString(le));
   return check_launch("moe_hist_accumulate");
+}
+
+size_t moe_expert_permutation_workspace_bytes(int T, int E) {
+  (void)T;
+  return static_cast<size_t>((E + 31) / 32 * 32) * moe::kPermMaxSegments * sizeof(int);
+}
+
+int moe_expert_permutation(const uint32_t* active_bits, int T, int E, int k, int row_pad, int* perm_offsets, int* perm_counts,
+                           int* perm_tokens, int* slot_pos, void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace moe;
+  MOE_REQUIRE(T >= 0 && E >= 1 && E <= 1024 && k >= 0 && k <= E && row_pad >= 1 && row_pad <= 256, MOE_ERR_INVALID_ARGUMENT,
+              "moe_expert_permutation: T=%d E=%d k=%d row_pad=%d", T, E, k, row_pad);
+  MOE_REQUIRE(perm_offsets && perm_counts && workspace, MOE_ERR_INVALID_ARGUMENT, "moe_expert_permutation: NULL offsets / counts / workspace");
+  MOE_REQUIRE(workspace_bytes >= moe_expert_permutation_workspace_bytes(T, E), MOE_ERR_INVALID_ARGUMENT,
+              "moe_expert_permutation: workspace of %zu bytes is too small", workspace_bytes);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (T == 0 || k == 0) {     // no token selects anything: every list is empty
+    cudaError_t e = cudaMemsetAsync(perm_offsets, 0, sizeof(int) * (E + 1), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(perm_counts, 0, sizeof(int) * E, st);
+    if (e != cudaSuccess) return fail(MOE_ERR_CUDA, "moe_expert_permutation: %s", cudaGetErrorString(e));
+    return MOE_OK;
+  }
+  MOE_REQUIRE(active_bits && perm_tokens && slot_pos, MOE_ERR_INVALID_ARGUMENT, "moe_expert_permutation: NULL bits / tokens / slot_pos");
+  PermArgs p = {};
+  p.bits = active_bits;
+  p.T = T;
+  p.E = E;
+  p.W = (E + 31) / 32;
+  p.k = k;
+  p.row_pad = row_pad;
+  int seg = (T + kPermMaxSegments - 1) / kPermMaxSegments;
+  seg = (seg + 255) / 256 * 256;            // whole 32-token groups per warp
+  if (seg < 2048) seg = 2048;
+  p.seg_tokens = seg;
+  p.n_segments = (T + seg - 1) / seg;
+  p.seg_counts = static_cast<int*>(workspace);
+  p.offsets = perm_offsets;
+  p.counts = perm_counts;
+  p.tokens = perm_tokens;
+  p.slot_pos = slot_pos;
+  dim3 grid(static_cast<unsigned>(p.W), static_cast<unsigned>(p.n_segments));
+  cudaError_t le = launch_pdl(perm_count_kernel, grid, dim3(kPermWarps * 32), 0, st, p);
+  if (le != cudaSuccess) return fail(MOE_ERR_CUDA, "moe_expert_permutation (count) launch: %s", cudaGetErrorString(le));
+  int rc = check_launch("moe_expert_permutation (count)");
+  if (rc) return rc;
+  le = launch_pdl(perm_scatter_kernel, grid, dim3(kPermWarps * 32), 0, st, p);
+  if (le != cudaSuccess) return fail(MOE_ERR_CUDA, "moe_expert_permutation (scatter) launch: %s", cudaGetErrorString(le));
+  return check_launch("moe_expert_permutation (scatter)");
+}
+
+int moe_router_topk_perm(const float* scores, const uint32_t* removed_bits, int k, uint32_t* active_bits, int16_t* idx,
+                         unsigned long long* hist, int* perm_offsets, int* perm_counts, int* perm_tokens, int* slot_pos,
+                         int row_pad, int T, int E, int count_begin, int count_end, void* workspace, size_t workspace_bytes,
+                         void* stream) {
+  using namespace moe;
+  MOE_REQUIRE(active_bits != nullptr || T == 0, MOE_ERR_INVALID_ARGUMENT, "moe_router_topk_perm: active_bits is required");
+  int rc = moe_router_topk_biased(scores, nullptr, removed_bits, k, active_bits, idx, hist, nullptr, nullptr, 0, 0, T, E,
+                                  count_begin, count_end, stream);
+  if (rc) return rc;
+  return moe_expert_permutation(active_bits, T, E, k, row_pad, perm_offsets, perm_counts, perm_tokens, slot_pos, workspace,
+                                workspace_bytes, stream);
 }
 
 static int colmax_grid_y(int rows) {

@@ -195,6 +195,62 @@ def ffn_fused(x, w1p, b1p, w2p, b2, n_experts: int, expert_size: int, k: int, ac
     return Y, H, scores, bits, idx
 
 
+class ExpertPermutation:
+    """Compacted token -> expert permutation (moe_expert_permutation): `tokens[offsets[e] : offsets[e] + counts[e]]`
+    = ascending tokens whose active set holds expert e (lists padded to 128 rows with -1); `slot_pos[t, j]` = row of
+    token t's j-th active expert, -1 beyond its active count."""
+
+    def __init__(self, offsets, counts, tokens, slot_pos, k):
+        self.offsets, self.counts, self.tokens, self.slot_pos, self.k = offsets, counts, tokens, slot_pos, k
+
+
+def expert_permutation(active_bits, n_experts: int, k: int, row_pad: int = 128) -> ExpertPermutation:
+    """active_bits int32 [T, W] (router_topk(..., want_bits=True)) -> ExpertPermutation (all int32, on the device)."""
+    lib = _lib.load()
+    T, W = active_bits.shape
+    _need(active_bits, torch.int32, "active_bits", (T, (n_experts + 31) // 32))
+    dev = active_bits.device
+    offsets = torch.empty(n_experts + 1, dtype=torch.int32, device=dev)
+    counts = torch.empty(n_experts, dtype=torch.int32, device=dev)
+    tokens = torch.empty(int(lib.moe_down_grouped_rows(T, k, n_experts)), dtype=torch.int32, device=dev)
+    slot_pos = torch.empty((T, max(k, 1)), dtype=torch.int32, device=dev)[:, :k]
+    ws = torch.empty(int(lib.moe_expert_permutation_workspace_bytes(T, n_experts)), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.moe_expert_permutation(_ptr(active_bits), T, n_experts, int(k), int(row_pad), _ptr(offsets), _ptr(counts),
+                                        _ptr(tokens), _ptr(slot_pos) if k > 0 else 0, _ptr(ws), ws.numel(), _stream(active_bits))
+    _lib.check(rc, "moe_expert_permutation")
+    return ExpertPermutation(offsets, counts, tokens, slot_pos, k)
+
+
+_grouped_ws = {}
+
+
+def down_grouped(H, perm: ExpertPermutation, w2p, b2, n_experts: int, expert_size: int, out=None):
+    """Grouped / gathered down-projection over the active experts only.  H bf16 [T, h] (need not be masked);
+    w2p bf16 [d, h]; b2 f32 [d] or None -> Y bf16 [T, d].  Expert size 64 only (MoeLibraryError code -2 otherwise)."""
+    lib = _lib.load()
+    T, h = H.shape
+    d = w2p.shape[0]
+    _need(H, torch.bfloat16, "H")
+    _need(w2p, torch.bfloat16, "w2p", (d, h))
+    if b2 is not None:
+        _need(b2, torch.float32, "b2", (d,))
+    Y = out if out is not None else torch.empty((T, d), dtype=torch.bfloat16, device=H.device)
+    _need(Y, torch.bfloat16, "out", (T, d))
+    nbytes = int(lib.moe_down_grouped_workspace_bytes(T, perm.k, n_experts, d))
+    key = (H.device.index, _stream(H))
+    ws = _grouped_ws.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=H.device)
+        _grouped_ws[key] = ws
+    with torch.cuda.device(H.device):
+        rc = lib.moe_down_grouped(_ptr(H), _ptr(perm.offsets), _ptr(perm.tokens), _ptr(perm.slot_pos) if perm.k > 0 else _ptr(perm.offsets),
+                                  _ptr(w2p), _ptr(b2), _ptr(Y), T, h, d, n_experts, int(expert_size), int(perm.k), _ptr(ws),
+                                  ws.numel(), _stream(H))
+    _lib.check(rc, "moe_down_grouped")
+    return Y
+
+
 def hist_accumulate(idx, n_experts: int, hist=None):
     """K4.  idx int16 (any shape) -> hist int64 [E] (accumulated in place if given)."""
     lib = _lib.load()

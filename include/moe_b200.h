@@ -73,9 +73,10 @@ MOE_API int moe_geglu_up(const void* x, const void* w1p, const float* b1p, const
                  int es, int act, void* stream);
 
 /*
- * K2 -- router: per-token top-k select over E expert scores (one warp per token, radix select
- * on order-preserving keys, ties to the lower expert id), fused with the selection histogram,
- * the score column-max and the in-place zeroing of H for unselected / removed experts.
+ * K2 -- router: per-token top-k select over E expert scores, fused with the selection histogram, the score
+ * column-max and the in-place zeroing of H for unselected / removed experts.  E <= 256: 4 / 8 / 16 lanes per token
+ * (several tokens per warp, warp shuffles), exact k-th largest order-preserving key from a bitonic sort; larger E: one
+ * warp per token, radix select over ballots.  Ties go to the lower expert id.
  *
  * Replaces: moefy.py:21-23 (topk, embedding(labels, patterns).sum, gate[mask==0]=0);
  * frequency_measure.py:52-57 (Python counter loop; integer counts instead of += 1/S);
@@ -103,6 +104,47 @@ MOE_API int moe_router_topk_biased(const float* scores, const float* score_bias,
                     int h, int es, int T, int E, int count_begin, int count_end, void* stream);
 
 /*
+ * Compacted token -> expert permutation (the north star's second router output).  From the expert-set words of
+ * moe_router_topk: for every expert e the ascending list of the tokens whose active set contains e,
+ *   perm_tokens[perm_offsets[e] + i], 0 <= i < perm_counts[e];
+ * every list is padded to a multiple of `row_pad` rows (pad entries -1; perm_offsets[E] = total padded rows), and
+ *   slot_pos[t * k + j] = row of token t's j-th active expert (ascending expert id), -1 for j >= its active count.
+ * A stable counting sort without atomics: the lists are deterministic and in token order.
+ * Replaces: the [T, k, h] gather `F.embedding(labels, patterns)` of moefy.py:22 as the data structure that says which
+ * neurons of which token are live -- here E lists of token ids instead of T*k one-hot rows.
+ *   active_bits u32 [T, W]   perm_offsets i32 [E + 1] out   perm_counts i32 [E] out
+ *   perm_tokens i32 [moe_down_grouped_rows(T, k, E)] out (for row_pad <= 128)   slot_pos i32 [T, k] out
+ *   workspace: moe_expert_permutation_workspace_bytes(T, E) bytes of device scratch (no initialisation needed)
+ * moe_router_topk_perm = moe_router_topk (bits + labels + histogram) followed by the permutation, one call.
+ */
+MOE_API int moe_expert_permutation(const uint32_t* active_bits, int T, int E, int k, int row_pad, int* perm_offsets,
+                    int* perm_counts, int* perm_tokens, int* slot_pos, void* workspace, size_t workspace_bytes, void* stream);
+MOE_API size_t moe_expert_permutation_workspace_bytes(int T, int E);
+MOE_API int moe_router_topk_perm(const float* scores, const uint32_t* removed_bits, int k, uint32_t* active_bits, int16_t* idx,
+                    unsigned long long* hist, int* perm_offsets, int* perm_counts, int* perm_tokens, int* slot_pos,
+                    int row_pad, int T, int E, int count_begin, int count_end, void* workspace, size_t workspace_bytes,
+                    void* stream);
+
+/*
+ * Grouped / gathered down-projection: Y[t] = b2 + sum over the token's active experts e of
+ * H[t, e*es : (e+1)*es] W2p[:, e*es : (e+1)*es]^T -- only the active experts' slices of H and W2 are read (tcgen05,
+ * one 128-token tile of one expert's list per CTA, A rows gathered with cp.async, W2 slice by TMA), fp32 partial rows
+ * combined per token in ascending expert order (deterministic).  Removed experts are absent from the lists, so the
+ * removal mask is applied by construction.  H need not be masked.
+ * Replaces: moefy.py:22-23 + the stock ff.net.2 Linear [upstream] (mask the gate, then a dense down-projection).
+ *   H bf16 [T, h]   perm_offsets / perm_tokens / slot_pos: from moe_expert_permutation with row_pad = 128
+ *   w2p bf16 [d, h]   b2 f32 [d] or NULL   Y bf16 [T, d] out
+ *   workspace: moe_down_grouped_workspace_bytes(T, k, E, d) bytes (fp32 partial rows; no initialisation needed)
+ * Requirements: es == 64 (one expert = one 64-wide bf16 k-block; BASELINE.json configs[0] geometry), d % 16 == 0;
+ * otherwise MOE_ERR_UNSUPPORTED_SHAPE (use moe_down_proj on the masked H).
+ */
+MOE_API int moe_down_grouped(const void* H, const int* perm_offsets, const int* perm_tokens, const int* slot_pos,
+                    const void* w2p, const float* b2, void* Y, int T, int h, int d, int E, int es, int k, void* workspace,
+                    size_t workspace_bytes, void* stream);
+MOE_API size_t moe_down_grouped_rows(int T, int k, int E);
+MOE_API size_t moe_down_grouped_workspace_bytes(int T, int k, int E, int d);
+
+/*
  * K3 -- down-projection Y = H W2p^T + b2 (tcgen05 / TMEM / TMA).  H has already been zeroed
  * for inactive experts by K2, so this is the dense-masked form; W2p may be the
  * Wanda-masked copy produced by moe_mask_weights.
@@ -122,8 +164,8 @@ MOE_API size_t moe_down_proj_workspace_bytes(int T, int h, int d);
 
 /*
  * K4 -- standalone expert-frequency histogram over stored labels:
- * hist[e] += #occurrences of e in idx[0:n] (vectorised loads, warp-aggregated shared-memory
- * bins, one 64-bit global atomic per bin per CTA).
+ * hist[e] += #occurrences of e in idx[0:n] (16-byte loads, per-warp shared-memory bins updated with
+ * native shared atomics, one 64-bit global atomic per bin per CTA).
  * Replaces: frequency_measure.py:53-57 applied to saved labels; the quantity that
  * freq_expert_select.py:61-64 averages and that is all-reduced across GPUs.
  */
@@ -183,8 +225,13 @@ MOE_API int moe_mask_vote(const uint32_t* masks, int T, long long n_words, float
  *              allocation (the kernel leaves its counters at zero); one workspace per concurrently running stream
  * Requirements: d % 64 == 0, h % 64 == 0, es % 4 == 0, E <= 512 and an expert size the tile shapes support;
  * otherwise MOE_ERR_UNSUPPORTED_SHAPE is returned and the caller uses the three separate entry points.
- * The kernel occupies every SM with one CTA and its CTAs wait on each other: it must not share the device with
- * a kernel that never finishes (all CUDA kernels of this library do finish).
+ * The kernel occupies every SM with one CTA and its CTAs wait on each other: the launch is refused
+ * (MOE_ERR_UNSUPPORTED_SHAPE) when cudaOccupancyMaxActiveClusters says the CTA pairs cannot all be resident (MPS
+ * thread limits, green contexts), and fused launches of one process on different streams of a device are ordered one
+ * after the other by the library (events) -- two such grids resident together would wait for SMs the other holds.
+ * A kernel of another library may run concurrently as long as it finishes (the pairs that found no SM start when it
+ * does); a cross-CTA wait of more than 2 s traps instead of hanging the GPU.  One process per GPU is the tested
+ * configuration; per-device caches (SM count, kernel attributes, ordering events) are keyed by the current device.
  */
 MOE_API int moe_ffn_fused(const void* x, const void* w1p, const float* b1p, const void* w2p, const float* b2, void* H,
                   float* scores, void* Y, const uint32_t* removed_bits, int k, uint32_t* active_bits, int16_t* idx,

@@ -1,0 +1,146 @@
+"""GPU: the north star's remaining router / down-projection forms:
+  * the several-tokens-per-warp router against the warp-per-token one and torch.topk,
+  * the compacted token -> expert permutation (moe_expert_permutation) against numpy,
+  * the grouped / gathered down-projection (moe_down_grouped) against the oracle and the dense-masked K3."""
+import numpy as np
+import pytest
+import torch
+
+import moe_b200 as M
+import moe_ffn_oracle as O
+from moe_b200 import _lib
+from moe_b200.packing import ExpertLayout, pack_ffn, bits_to_sets
+from gpu_util import DEV, rel_err, r16, OUT_REL_TOL, MARGIN_TOL
+
+pytestmark = pytest.mark.gpu
+
+
+def _route(scores, k, E, es, removed=None, bias=None, mask=True):
+    H = torch.ones(scores.shape[0], E * es, dtype=torch.bfloat16, device=DEV) if mask else None
+    hist = torch.zeros(E, dtype=torch.int64, device=DEV)
+    cmax = torch.full((E,), float("-inf"), device=DEV)
+    rb = None if not removed else M.bits_from_expert_list(removed, E).to(DEV)
+    bits, idx = M.router_topk(scores, k, removed_bits=rb, want_idx=True, hist=hist, colmax_out=cmax, H=H, expert_size=es,
+                              count_rows=(3, scores.shape[0] - 2), score_bias=bias)
+    torch.cuda.synchronize()
+    return bits.cpu(), idx.cpu(), hist.cpu(), cmax.cpu(), None if H is None else H.cpu()
+
+
+@pytest.mark.parametrize("Tn,E,es,k", [(1000, 64, 20, 19), (777, 20, 64, 6), (513, 128, 20, 38), (300, 256, 20, 76),
+                                        (90, 256, 4, 255), (64, 8, 16, 3), (200, 40, 8, 12), (33, 96, 4, 1)])
+def test_multi_token_router_equals_warp_per_token_router(lib, monkeypatch, Tn, E, es, k):
+    g = torch.Generator().manual_seed(E + k)
+    scores = torch.randn(Tn, E, generator=g)
+    scores[::4] = torch.round(scores[::4] * 2) / 2          # many exact ties
+    scores[1::7] = scores[1::7].abs() * 3 + 1               # shared sign / exponent prefixes
+    dsc = scores.to(DEV)
+    removed = sorted(set(int(v) for v in torch.randint(0, E, (max(1, E // 10),), generator=g)))
+    bias = (torch.rand(E, generator=g) * (torch.rand(E, generator=g) < 0.2)).to(DEV)
+    for rm, bs in ((None, None), (removed, None), (None, bias), (removed, bias)):
+        monkeypatch.setenv("MOE_ROUTER_LEGACY", "1")
+        ref = _route(dsc, k, E, es, rm, bs)
+        monkeypatch.setenv("MOE_ROUTER_LEGACY", "0")
+        new = _route(dsc, k, E, es, rm, bs)
+        for a, b, what in zip(ref, new, ("bits", "idx", "hist", "colmax", "H")):
+            assert torch.equal(a, b), (what, rm is not None, bs is not None)
+    # and against torch.topk on the plain scores: ascending ids, ties to the lowest id
+    new = _route(dsc, k, E, es, mask=False)
+    want = torch.topk(scores, k, dim=-1)[1].sort(dim=-1)[0]
+    srt = torch.sort(scores, dim=-1, descending=True)[0]
+    clear = (srt[:, k - 1] > srt[:, k]) if k < E else torch.ones(Tn, dtype=torch.bool)
+    assert torch.equal(new[1].long()[clear], want[clear])
+    assert torch.equal(new[3], scores.max(0)[0])
+
+
+def test_router_above_256_experts_uses_the_warp_per_token_kernel(lib):
+    E, k = 320, 50
+    scores = torch.randn(70, E, generator=torch.Generator().manual_seed(1))
+    bits, idx = M.router_topk(scores.to(DEV), k, want_idx=True)
+    assert torch.equal(idx.cpu().long(), torch.topk(scores, k, dim=-1)[1].sort(dim=-1)[0])
+
+
+def _numpy_permutation(sets, E, k, pad):
+    lists = [[t for t, s in enumerate(sets) if e in s] for e in range(E)]
+    offsets = [0]
+    for lst in lists:
+        offsets.append(offsets[-1] + (len(lst) + pad - 1) // pad * pad)
+    return lists, offsets
+
+
+@pytest.mark.parametrize("Tn,E,k,pad", [(1, 8, 2, 128), (300, 20, 6, 128), (5000, 64, 19, 128), (9000, 256, 76, 128),
+                                         (4097, 96, 3, 128), (2500, 40, 40, 32), (130, 33, 0, 128)])
+def test_expert_permutation_matches_numpy(lib, Tn, E, k, pad):
+    g = torch.Generator().manual_seed(Tn + E)
+    scores = torch.randn(Tn, E, generator=g).to(DEV)
+    removed = [1, E - 1] if E > 8 else None
+    rb = None if removed is None else M.bits_from_expert_list(removed, E).to(DEV)
+    bits, _ = M.router_topk(scores, k, removed_bits=rb)
+    perm = M.expert_permutation(bits, E, k, row_pad=pad)
+    torch.cuda.synchronize()
+    sets = bits_to_sets(bits, E)
+    lists, offsets = _numpy_permutation(sets, E, k, pad)
+    assert perm.offsets.cpu().tolist() == offsets
+    assert perm.counts.cpu().tolist() == [len(l) for l in lists]
+    tokens = perm.tokens.cpu().numpy()
+    for e in range(E):
+        seg = tokens[offsets[e]:offsets[e + 1]]
+        assert seg[:len(lists[e])].tolist() == lists[e], e           # ascending token order, deterministic
+        assert (seg[len(lists[e]):] == -1).all()
+    sp = perm.slot_pos.cpu().numpy()
+    for t in range(0, Tn, max(1, Tn // 200)):
+        act = sorted(sets[t])
+        for j, e in enumerate(act):
+            assert tokens[sp[t, j]] == t and offsets[e] <= sp[t, j] < offsets[e] + len(lists[e])
+        assert (sp[t, len(act):] == -1).all()
+    if removed is not None:
+        assert all(len(lists[e]) == 0 for e in removed)        # removed experts own no tokens
+
+
+@pytest.mark.parametrize("d,h,shape,ratio,removed", [(64, 256, (2, 96), 0.5, None), (128, 512, (1, 300), 0.3, [1, 5]),
+                                                       (320, 1280, (2, 1000), 0.3, None), (320, 1280, (1, 4096), 0.3, [0, 7, 13]),
+                                                       (640, 2560, (2, 333), 0.3, None)])
+def test_grouped_down_projection_matches_dense_and_oracle(lib, d, h, shape, ratio, removed):
+    """es = 64 (BASELINE-literal geometry): router -> permutation -> grouped down-projection on the UNMASKED H equals
+    the dense-masked K3 on the masked H (same bf16 inputs, fp32 accumulation) and the oracle within 1e-2."""
+    es = 64
+    layer = O.synthetic_layer(d, h, shape, es, seed=d + shape[1])
+    lay = ExpertLayout.from_labels(layer["labels"])
+    E = lay.n_experts
+    k = O.topk_from_ratio(E, ratio)
+    p = pack_ffn(lay, layer["w1"], layer["b1"], layer["w2"], layer["b2"], device=DEV)
+    xt = layer["x"].reshape(-1, d).to(DEV, torch.bfloat16).contiguous()
+    H, scores, _ = M.geglu_up(xt, p.w1p, p.b1p, E, es)
+    rb = None if not removed else M.bits_from_expert_list(removed, E).to(DEV)
+    bits, _ = M.router_topk(scores, k, removed_bits=rb)
+    perm = M.expert_permutation(bits, E, k)
+    y_grouped = M.down_grouped(H, perm, p.w2p, p.b2, E, es)
+    Hm = H.clone()
+    M.router_topk(scores, k, removed_bits=rb, want_bits=False, H=Hm, expert_size=es)
+    y_dense = M.down_proj(Hm, p.w2p, p.b2)
+    torch.cuda.synchronize()
+    assert rel_err(y_grouped.float(), y_dense.float()) < 4e-3           # both bf16-rounded from fp32 sums
+    pat = O.patterns_from_labels(layer["labels"])
+    x16, w1, w2 = r16(layer["x"]), r16(layer["w1"]), r16(layer["w2"])
+    if removed:
+        Ho, _, _, sc = O.remove_experts_forward(x16, w1, layer["b1"], pat, k, removed, 0)
+    else:
+        Ho, _, _, sc = O.moefy_forward(x16, w1, layer["b1"], pat, k)
+    safe = (O.topk_margin(sc, k) > MARGIN_TOL).numpy()
+    yo = O.down_proj(r16(Ho), w2, layer["b2"]).reshape(len(safe), -1)
+    assert safe.mean() > 0.85
+    assert rel_err(y_grouped.float().cpu()[safe], yo[safe]) < OUT_REL_TOL
+
+
+def test_grouped_down_projection_rejects_other_expert_sizes(lib):
+    H = torch.zeros(128, 320, dtype=torch.bfloat16, device=DEV)
+    bits = torch.zeros(128, 1, dtype=torch.int32, device=DEV)
+    perm = M.expert_permutation(bits, 16, 4)
+    w2 = torch.zeros(64, 320, dtype=torch.bfloat16, device=DEV)
+    with pytest.raises(_lib.MoeLibraryError, match="code -2"):
+        M.down_grouped(H, perm, w2, None, 16, 20)
+    # empty token shard: both entry points are no-ops
+    e = M.expert_permutation(torch.zeros(0, 1, dtype=torch.int32, device=DEV), 16, 4)
+    assert e.offsets.cpu().tolist() == [0] * 17
+    y = M.down_grouped(torch.zeros(0, 1024, dtype=torch.bfloat16, device=DEV), e,
+                       torch.zeros(64, 1024, dtype=torch.bfloat16, device=DEV), None, 16, 64)
+    assert y.shape == (0, 64)
