@@ -246,72 +246,91 @@ def time_graph(g, n):
 
 
 def aux_rooflines(M, args, dev, hbm_gbs, peak_src):
-    """K2 router_topk_kernel and K4 hist_accumulate_kernel against HBM at the UNet-batch-16 shapes (BASELINE
-    configs[2]): the 16 layers' score / hidden-state buffers total 1.6 GB, far beyond L2, so every launch streams from
-    and to HBM.  Algorithmic bytes per token: K2 reads 4 E (scores), writes 2 k (labels) and the
-    zero stores of the masking, 2 es (E - k); K4 reads 2 k (labels).  Times: CUDA events around a graph holding
-    exactly those 16 launches."""
+    """K2 router_multi_kernel and K4 hist_accumulate_kernel against HBM at the UNet-batch-16 shape of the d = 320
+    layers (BASELINE configs[2]: T = 65 536 tokens, the shape that dominates a batch-16 step), each kernel timed alone
+    (CUDA events around a graph of launches over REP distinct buffer sets, so nothing is L2-resident between launches),
+    plus the 16-launch sweep over all layer shapes of one batch-16 step.  Algorithmic bytes per token (DESIGN.md
+    section 4): K2 reads 4 E (scores), writes 2 k (labels) or, when masking, the zero stores 2 es (E - k); K4 reads
+    2 k (labels)."""
     B = 16
     gen = torch.Generator(device=dev).manual_seed(7)
+    d0, h0, s0 = layer_list()[0]
+    es0 = expert_size_for(args.experts, h0)
+    E0, T0 = h0 // es0, B * s0
+    k0 = int(E0 * RATIO)
+    REP = 4
+    bufs = [dict(scores=torch.randn(T0, E0, generator=gen, device=dev),
+                 H=torch.empty(T0, h0, dtype=torch.bfloat16, device=dev).normal_(generator=gen),
+                 hist=torch.zeros(E0, dtype=torch.int64, device=dev)) for _ in range(REP)]
+
+    def router_mask():
+        for b in bufs:
+            M.router_topk(b["scores"], k0, want_bits=False, want_idx=False, hist=b["hist"], H=b["H"], expert_size=es0,
+                          count_rows=(0, s0))
+
+    idx = []
+
+    def router_select():
+        idx.clear()
+        for b in bufs:
+            _, ix = M.router_topk(b["scores"], k0, want_bits=False, want_idx=True)
+            idx.append(ix)
+
+    router_mask(); router_select()
+    torch.cuda.synchronize()
+    us_mask = time_graph(graph_of(router_mask, dev), 10) / REP * 1e3
+    us_sel = time_graph(graph_of(router_select, dev), 10) / REP * 1e3
+    by_mask = T0 * (4 * E0 + 2 * es0 * (E0 - k0))
+    by_sel = T0 * (4 * E0 + 2 * k0)
+    shape = f"T={T0} E={E0} es={es0} k={k0}"
+    r_router = dict(bound="hbm", kernel="router_multi_kernel (K2: select + histogram + write-only masking of H)", shape=shape,
+                    achieved=round(by_mask / us_mask / 1e3, 1), peak=hbm_gbs, unit="GB/s",
+                    frac=round(by_mask / us_mask / 1e3 / hbm_gbs, 4), us_per_launch=round(us_mask, 2),
+                    # ncu --set full of this launch (profiles/r02_ncu_aux_kernels.csv): dram read + write bytes
+                    traffic=1.65e8, peak_source=peak_src,
+                    algorithmic=f"per token 4E bytes of scores read + 2 es (E - k) bytes of zero stores = {by_mask / 1e6:.0f} MB per launch",
+                    select_only=dict(achieved=round(by_sel / us_sel / 1e3, 1), unit="GB/s", frac=round(by_sel / us_sel / 1e3 / hbm_gbs, 4),
+                                     us_per_launch=round(us_sel, 2), traffic=1.68e7,
+                                     algorithmic=f"per token 4E read + 2k labels written = {by_sel / 1e6:.0f} MB per launch",
+                                     note="bound by the sorting network (integer pipe: ~300 warp instructions per token, "
+                                          "ncu source page), not by HBM"))
+    # K4 over the labels of 144 prompt batches of this layer (configs[3] accumulation): 0.36 GB of int16 labels
+    big = idx[0].repeat(144, 1)
+    hist = torch.zeros(E0, dtype=torch.int64, device=dev)
+
+    def hist_fn():
+        M.hist_accumulate(big, E0, hist)
+
+    hist_fn()
+    torch.cuda.synchronize()
+    us_h = time_graph(graph_of(hist_fn, dev), 10) * 1e3
+    by_h = big.numel() * 2
+    r_hist = dict(bound="hbm", kernel="hist_accumulate_kernel (K4)", shape=f"{big.numel()} labels, E={E0}",
+                  achieved=round(by_h / us_h / 1e3, 1), peak=hbm_gbs, unit="GB/s", frac=round(by_h / us_h / 1e3 / hbm_gbs, 4),
+                  traffic=None, peak_source=peak_src, us_per_launch=round(us_h, 2),
+                  algorithmic=f"2 bytes per (token, slot) label read: {by_h / 1e6:.0f} MB per launch")
+    del big
+    # the 16 router launches of one batch-16 step (all layer shapes; the small-T layers are launch-latency-bound)
     cells = []
     for (d, h, s) in layer_list():
         es = expert_size_for(args.experts, h)
         E, T = h // es, B * s
-        k = int(E * RATIO)
-        scores = torch.randn(T, E, generator=gen, device=dev)
-        H = torch.empty(T, h, dtype=torch.bfloat16, device=dev).normal_(generator=gen)
-        cells.append(dict(T=T, E=E, es=es, k=k, scores=scores, H=H, hist=torch.zeros(E, dtype=torch.int64, device=dev), s=s))
+        cells.append(dict(T=T, E=E, es=es, k=int(E * RATIO), s=s, scores=torch.randn(T, E, generator=gen, device=dev),
+                          H=torch.empty(T, h, dtype=torch.bfloat16, device=dev).normal_(generator=gen),
+                          hist=torch.zeros(E, dtype=torch.int64, device=dev)))
 
-    def router():
+    def sweep():
         for c in cells:
             M.router_topk(c["scores"], c["k"], want_bits=False, want_idx=False, hist=c["hist"], H=c["H"],
                           expert_size=c["es"], count_rows=(0, c["s"]))
 
-    router()
+    sweep()
     torch.cuda.synchronize()
-    ms = time_graph(graph_of(router, dev), 10)
+    ms = time_graph(graph_of(sweep, dev), 10)
     by = sum(c["T"] * (4 * c["E"] + 2 * c["es"] * (c["E"] - c["k"])) for c in cells)
-    r_router = dict(bound="hbm", kernel="router_topk_kernel (K2: select + histogram + write-only masking of H)",
-                    achieved=round(by / (ms * 1e-3) / 1e9, 1), peak=hbm_gbs, unit="GB/s",
-                    frac=round(by / (ms * 1e-3) / 1e9 / hbm_gbs, 4), traffic=None, peak_source=peak_src,
-                    algorithmic="per token 4E bytes of scores read + 2 es (E - k) bytes of zero stores; 16 launches at UNet "
-                                f"batch {B} = {by / 1e6:.0f} MB per sweep", ms_per_sweep=round(ms, 4))
-    # select-only form (labels out, no masking): what the permutation / grouped down-projection path consumes
-    idx = []
-
-    def select():
-        idx.clear()
-        for c in cells:
-            _, ix = M.router_topk(c["scores"], c["k"], want_bits=False, want_idx=True)
-            idx.append(ix)
-
-    select()
-    torch.cuda.synchronize()
-    labels = [ix.clone() for ix in idx]
-    ms_sel = time_graph(graph_of(select, dev), 10)
-    by_sel = sum(c["T"] * (4 * c["E"] + 2 * c["k"]) for c in cells)
-    r_router["select_only"] = dict(achieved=round(by_sel / (ms_sel * 1e-3) / 1e9, 1), unit="GB/s",
-                                   frac=round(by_sel / (ms_sel * 1e-3) / 1e9 / hbm_gbs, 4), ms_per_sweep=round(ms_sel, 4),
-                                   algorithmic=f"per token 4E read + 2k labels written = {by_sel / 1e6:.0f} MB per sweep "
-                                               "(working set 0.2 GB > L2)")
-    # K4 over the labels of 24 prompt batches of the d=320 layers (configs[3] accumulation): 0.36 GB of int16 labels
-    big = labels[0].repeat(24, 1)
-    hist = torch.zeros(cells[0]["E"], dtype=torch.int64, device=dev)
-
-    def hist_fn():
-        M.hist_accumulate(big, cells[0]["E"], hist)
-        for c, ix in zip(cells, labels):
-            M.hist_accumulate(ix, c["E"], c["hist"])
-
-    hist_fn()
-    torch.cuda.synchronize()
-    ms_h = time_graph(graph_of(hist_fn, dev), 10)
-    by_h = big.numel() * 2 + sum(ix.numel() * 2 for ix in labels)
-    r_hist = dict(bound="hbm", kernel="hist_accumulate_kernel (K4)", achieved=round(by_h / (ms_h * 1e-3) / 1e9, 1),
-                  peak=hbm_gbs, unit="GB/s", frac=round(by_h / (ms_h * 1e-3) / 1e9 / hbm_gbs, 4), traffic=None,
-                  peak_source=peak_src, ms_per_sweep=round(ms_h, 4),
-                  algorithmic=f"2 bytes per (token, slot) label read: {by_h / 1e6:.0f} MB per sweep (one 0.36 GB label "
-                              "buffer = 24 prompt batches of a d=320 layer, + the 16 per-layer buffers of one batch-16 step)")
+    r_router["sweep_16_layers"] = dict(achieved=round(by / (ms * 1e-3) / 1e9, 1), unit="GB/s", ms_per_sweep=round(ms, 4),
+                                       frac=round(by / (ms * 1e-3) / 1e9 / hbm_gbs, 4),
+                                       algorithmic=f"{by / 1e6:.0f} MB over the 16 launches of one UNet-batch-{B} step")
     return r_router, r_hist
 
 

@@ -302,7 +302,7 @@ static cudaError_t launch_multi(const RouterGeom& g, const RouterPtrs& a, int gr
 // the token's active count).  Deterministic: a stable counting sort -- per (word, token segment, warp) counts, then an
 // ordered scatter -- no atomics.  Grid (words, segments); warp q of a CTA owns a contiguous token sub-range.
 constexpr int kPermWarps = 8;
-constexpr int kPermMaxSegments = 16;
+constexpr int kPermMaxSegments = 64;
 
 struct PermArgs {
   const uint32_t* bits;   // [T, W]
@@ -440,27 +440,52 @@ __global__ void __launch_bounds__(kPermWarps * 32) perm_scatter_kernel(const Per
 }
 
 // ------------------------------------------------------------------ K4 standalone histogram
-// 16-byte loads (8 labels), per-warp private shared-memory bins updated with native shared atomics (no return value:
-// RED.shared), folded and flushed with one int64 global atomic per expert per CTA.  (The round-1 kernel aggregated
-// equal labels with __match_any_sync first: ~16 match instructions per 16 bytes, 159 GB/s = 2 % of HBM.)
-constexpr int kHistWarps = 8;
+// 16-byte loads (8 labels per thread and load, four loads in flight), THREAD-PRIVATE 16-bit counters in shared memory
+// laid out [expert][thread]: a thread only ever touches its own column, so counting is a plain load / add / store --
+// no atomics, no match / ballot aggregation, at most a 2-way bank conflict (two 16-bit columns per bank) -- folded
+// once per CTA into one int64 global atomic per expert.  The grid is sized so that a thread counts at most
+// kHistMaxPerThread labels: a 16-bit counter cannot wrap.  (Round 1 aggregated equal labels with __match_any_sync first, 16 match
+// instructions per 16 bytes: 159 GB/s; per-warp bins with shared atomics: 921 GB/s.)
+constexpr int kHistThreads = 128;
+constexpr int kHistMaxPerThread = 60000;
 
-__global__ void __launch_bounds__(kHistWarps * 32) hist_accumulate_kernel(const int16_t* __restrict__ idx, long long n, int E,
-                                                                          int copies, unsigned long long* __restrict__ hist) {
-  extern __shared__ unsigned int bins[];      // [copies][E]: warp q updates copy q % copies
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < copies * E; i += blockDim.x) bins[i] = 0u;
+__global__ void __launch_bounds__(kHistThreads) hist_accumulate_kernel(const int16_t* __restrict__ idx, long long n, int E,
+                                                                       unsigned long long* __restrict__ hist) {
+  extern __shared__ unsigned short cnt[];      // [E][kHistThreads]
+  for (int i = threadIdx.x; i < E * kHistThreads / 2; i += blockDim.x) reinterpret_cast<unsigned int*>(cnt)[i] = 0u;
   __syncthreads();
   pdl_wait();
   pdl_launch_dependents();
-  unsigned int* mine = bins + (warp % copies) * E;
+  unsigned short* mine = cnt + threadIdx.x;
   const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
   const bool aligned = (reinterpret_cast<uintptr_t>(idx) & 15) == 0;
   const long long nvec = aligned ? (n >> 3) : 0;  // 8 labels per 16-byte load
   const int4* v4 = reinterpret_cast<const int4*>(idx);
   auto add = [&](int v) {
-    if (v >= 0 && v < E) atomicAdd(mine + v, 1u);
+    if (v >= 0 && v < E) mine[v * kHistThreads] += 1;
+  };
+  auto add8 = [&](const int4& q) {
+    const int wv[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      add(static_cast<int16_t>(wv[c] & 0xffff));
+      add(static_cast<int16_t>((wv[c] >> 16) & 0xffff));
+    }
+  };
+  auto fold = [&]() {
+    __syncthreads();
+    for (int e = threadIdx.x; e < E; e += blockDim.x) {
+      unsigned int tot = 0;
+      const unsigned int* row = reinterpret_cast<const unsigned int*>(cnt + e * kHistThreads);
+      // rotate the start so that the threads of a warp (consecutive experts) read different banks
+      for (int i = 0; i < kHistThreads / 2; ++i) {
+        const unsigned int w = row[(i + e) & (kHistThreads / 2 - 1)];
+        tot += (w & 0xffffu) + (w >> 16);
+      }
+      if (tot) atomicAdd(hist + e, static_cast<unsigned long long>(tot));
+    }
+    __syncthreads();
   };
   long long i = tid;
   for (; i + 3 * nthreads < nvec; i += 4 * nthreads) {     // four loads in flight per thread
@@ -468,32 +493,11 @@ __global__ void __launch_bounds__(kHistWarps * 32) hist_accumulate_kernel(const 
 #pragma unroll
     for (int u = 0; u < 4; ++u) q[u] = __ldg(v4 + i + u * nthreads);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int wv[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        add(static_cast<int16_t>(wv[c] & 0xffff));
-        add(static_cast<int16_t>((wv[c] >> 16) & 0xffff));
-      }
-    }
+    for (int u = 0; u < 4; ++u) add8(q[u]);
   }
-  for (; i < nvec; i += nthreads) {
-    const int4 q = __ldg(v4 + i);
-    const int wv[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      add(static_cast<int16_t>(wv[c] & 0xffff));
-      add(static_cast<int16_t>((wv[c] >> 16) & 0xffff));
-    }
-  }
+  for (; i < nvec; i += nthreads) add8(__ldg(v4 + i));
   for (long long j = (nvec << 3) + tid; j < n; j += nthreads) add(static_cast<int>(idx[j]));
-  (void)lane;
-  __syncthreads();
-  for (int e = threadIdx.x; e < E; e += blockDim.x) {
-    unsigned int tot = 0;
-    for (int w = 0; w < copies; ++w) tot += bins[w * E + e];
-    if (tot) atomicAdd(hist + e, static_cast<unsigned long long>(tot));
-  }
+  fold();
 }
 
 // ------------------------------------------------------------------ column max over tokens
@@ -579,6 +583,10 @@ int moe_router_topk_biased(const float* scores, const float* score_bias, const u
     RouterGeom g = {};
     int L = 4;
     while (L < 32 && (E + L - 1) / L > 16) L <<= 1;
+    if (const char* le_env = getenv("MOE_ROUTER_LANES")) {      // experiments: more lanes per token, fewer keys per lane
+      const int v = atoi(le_env);
+      if ((v == 8 || v == 16 || v == 32) && v > L) L = v;
+    }
     int kpt = 1;
     while (kpt * L < E) kpt <<= 1;
     g.lanes = L;
@@ -629,17 +637,23 @@ int moe_router_topk_biased(const float* scores, const float* score_bias, const u
 
 int moe_hist_accumulate(const int16_t* idx, long long n, int E, unsigned long long* hist, void* stream) {
   using namespace moe;
-  MOE_REQUIRE(n >= 0 && E >= 1 && E <= 8192, MOE_ERR_INVALID_ARGUMENT, "moe_hist_accumulate: n=%lld E=%d", n, E);
+  MOE_REQUIRE(n >= 0 && E >= 1, MOE_ERR_INVALID_ARGUMENT, "moe_hist_accumulate: n=%lld E=%d", n, E);
   if (n == 0) return MOE_OK;
   MOE_REQUIRE(idx != nullptr && hist != nullptr, MOE_ERR_INVALID_ARGUMENT, "moe_hist_accumulate: NULL pointer");
-  const long long per_cta = 256LL * 8 * 8;  // 8 vector loads of 8 labels per thread
+  MOE_REQUIRE(E <= 768, MOE_ERR_UNSUPPORTED_SHAPE, "moe_hist_accumulate: E=%d > 768 bins (thread-private counters exceed shared memory)", E);
+  const size_t smem = static_cast<size_t>(E) * kHistThreads * sizeof(unsigned short);
+  int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(hist_accumulate_kernel), smem);
+  if (rc) return rc;
+  const long long per_cta = static_cast<long long>(kHistThreads) * 8 * 8;  // 8 vector loads of 8 labels per thread
   long long ctas = (n + per_cta - 1) / per_cta;
-  const long long max_ctas = static_cast<long long>(sm_count()) * 8;
+  const int per_sm = smem > 0 ? static_cast<int>((200 * 1024) / smem) : 16;
+  const long long max_ctas = static_cast<long long>(sm_count()) * (per_sm < 1 ? 1 : (per_sm > 16 ? 16 : per_sm));
   if (ctas > max_ctas) ctas = max_ctas;
-  const int copies = E <= 1024 ? kHistWarps : 1;       // private bins per warp while they fit 32 KB
-  cudaError_t le = launch_pdl(hist_accumulate_kernel, dim3(static_cast<unsigned>(ctas)), dim3(kHistWarps * 32),
-                              static_cast<size_t>(copies) * E * sizeof(unsigned int), static_cast<cudaStream_t>(stream), idx, n, E,
-                              copies, hist);
+  const long long min_ctas = (n + static_cast<long long>(kHistThreads) * kHistMaxPerThread - 1) / (static_cast<long long>(kHistThreads) * kHistMaxPerThread);
+  if (ctas < min_ctas) ctas = min_ctas;       // 16-bit thread-private counters: bound the labels per thread
+  MOE_REQUIRE(ctas <= 0x7fffffffLL, MOE_ERR_UNSUPPORTED_SHAPE, "moe_hist_accumulate: n=%lld too large", n);
+  cudaError_t le = launch_pdl(hist_accumulate_kernel, dim3(static_cast<unsigned>(ctas)), dim3(kHistThreads), smem,
+                              static_cast<cudaStream_t>(stream), idx, n, E, hist);
   if (le != cudaSuccess) return fail(MOE_ERR_CUDA, "moe_hist_accumulate launch: %s", cudaGetErrorString(le));
   return check_launch("moe_hist_accumulate");
 }
@@ -674,7 +688,7 @@ int moe_expert_permutation(const uint32_t* active_bits, int T, int E, int k, int
   p.row_pad = row_pad;
   int seg = (T + kPermMaxSegments - 1) / kPermMaxSegments;
   seg = (seg + 255) / 256 * 256;            // whole 32-token groups per warp
-  if (seg < 2048) seg = 2048;
+  if (seg < 256) seg = 256;
   p.seg_tokens = seg;
   p.n_segments = (T + seg - 1) / seg;
   p.seg_counts = static_cast<int*>(workspace);
