@@ -1,5 +1,12 @@
 """Host<->device copy ceilings for the e2e leg of bench.py: the same 16 layer-sized pinned buffers copied H2D only,
-D2H only and both directions at once (two streams), timed with CUDA events.  Run on the GPU box."""
+D2H only and both directions at once (two streams), timed with CUDA events.  Run on the GPU box.
+
+    python tools/pcie_probe.py                                   # one GPU
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 --master-port P tools/pcie_probe.py
+                                                                 # N ranks copying CONCURRENTLY (no kernels running):
+                                                                 # per-rank and aggregate GB/s = the host-side ceiling"""
+import os
+
 import torch
 
 SHAPES = [(8192, 320)] * 6 + [(2048, 640)] * 5 + [(512, 1280)] * 4 + [(128, 1280)]
@@ -19,7 +26,13 @@ def timed(fn, reps=20):
 
 
 def main():
-    dev = torch.device("cuda:0")
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
     host_in = [torch.empty(s, dtype=torch.bfloat16).pin_memory() for s in SHAPES]
     host_out = [torch.empty(s, dtype=torch.bfloat16).pin_memory() for s in SHAPES]
     dev_in = [torch.empty(s, dtype=torch.bfloat16, device=dev) for s in SHAPES]
@@ -47,8 +60,24 @@ def main():
         cur.wait_stream(s2)
 
     for name, fn in (("H2D only", h2d), ("D2H only", d2h), ("both directions", both)):
-        ms = timed(fn)
-        print(f"{name:16s}: {ms:.3f} ms for {nbytes / 1e6:.1f} MB per direction = {nbytes / ms / 1e6:.1f} GB/s per direction")
+        if world > 1:
+            dist.barrier()              # all ranks copy at the same time
+        ms = timed(fn, reps=50)
+        gbs = nbytes / ms / 1e6
+        if world > 1:
+            t = torch.tensor([gbs, ms], dtype=torch.float64, device=dev)
+            allv = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(allv, t)
+            if rank == 0:
+                per = [float(v[0]) for v in allv]
+                print(f"{name:16s}: {world} ranks concurrently, {nbytes / 1e6:.1f} MB per direction and rank: per rank "
+                      f"{min(per):.1f} .. {max(per):.1f} GB/s per direction, aggregate {sum(per):.1f} GB/s per direction "
+                      f"(slowest rank {max(float(v[1]) for v in allv):.3f} ms)", flush=True)
+        else:
+            print(f"{name:16s}: {ms:.3f} ms for {nbytes / 1e6:.1f} MB per direction = {gbs:.1f} GB/s per direction")
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
