@@ -31,6 +31,8 @@ SIGNATURES = {
     "moe_mask_vote": (c_int, [c_void_p, c_int, c_ll, c_float, c_void_p, c_void_p]),
     "moe_down_proj": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, ctypes.c_size_t,
                               c_void_p]),
+    "moe_down_proj_masked": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
+                                     ctypes.c_size_t, c_void_p]),
     "moe_down_proj_workspace_bytes": (ctypes.c_size_t, [c_int, c_int, c_int]),
     "moe_hist_accumulate": (c_int, [c_void_p, c_ll, c_int, c_void_p, c_void_p]),
     "moe_colmax_f32": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),

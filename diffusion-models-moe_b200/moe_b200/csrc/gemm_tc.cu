@@ -55,6 +55,7 @@ struct PipeBarriers {
   uint64_t empty[kMaxStages];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
+  uint64_t masked[kMaxStages];   // weight-masked down-projection: the masker warp has edited the landed B tile
   uint32_t tmem_base;
 };
 
@@ -252,7 +253,7 @@ __device__ __forceinline__ void producer_loop(const CUtensorMap* tmap_a, const C
   }
 }
 
-template <bool PAIR>
+template <bool PAIR, bool MASK = false>
 __device__ __forceinline__ void mma_loop(uint8_t* smem, PipeBarriers* bars, const GemmShape& g, uint32_t tmem_base,
                                          int rn, int rm) {
   constexpr bool pair = PAIR;
@@ -277,7 +278,8 @@ __device__ __forceinline__ void mma_loop(uint8_t* smem, PipeBarriers* bars, cons
     const uint32_t d_tmem = tmem_base + as * kAccStride;
     for (int kb = t.kb_begin; kb < t.kb_end; kb += g.ks) {
       const long long t0 = prof ? clock64() : 0;
-      tc::mbar_wait(&bars->full[s], ph);
+      // (weight-masked down-projection: the stage is ready once the masker warp has zeroed the masked weights)
+      tc::mbar_wait(MASK ? &bars->masked[s] : &bars->full[s], ph);
       tc::fence_after_thread_sync();
       const long long t1 = prof ? clock64() : 0;
       c_full += t1 - t0;
@@ -362,6 +364,7 @@ __device__ __forceinline__ PipeBarriers* setup_pipeline(uint8_t*& smem, uint8_t*
     for (int i = 0; i < g.stages; ++i) {
       tc::mbar_init(&bars->full[i], 1);
       tc::mbar_init(&bars->empty[i], PAIR ? 1u : static_cast<uint32_t>(g.cn + g.cm - 1));
+      tc::mbar_init(&bars->masked[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       tc::mbar_init(&bars->tmem_full[i], 1);
@@ -605,9 +608,91 @@ struct DownArgs {
   int d;
   float* ws_partial;   // split-K: [split_k][T][d] fp32 partial sums
   int* ws_counters;    // split-K: one arrival counter per output tile (kept at zero between calls)
+  const uint32_t* mask_bits;   // weight-masked form: bit (r * h + c) set = W2[r, c] is removed; else null
+  int h;
 };
 
-template <int CH, bool PAIR>
+// Weight-masked down-projection (WandaRemoveNeuronsFast): warp 2 edits every landed W2 tile in shared memory --
+// a 16-bit zero store per set mask bit (Wanda masks are 2-12 % dense) -- between the TMA's `full` and the MMA
+// thread's `masked` barrier, so the masked weights never exist in global memory: DRAM traffic per call = W2 + the
+// mask bits (d h / 8 bytes), against W2 read + masked copy written + masked copy read for moe_mask_weights + K3.
+// The bit words of the NEXT stage are fetched into registers before the current stage is waited for (one L2 / HBM
+// round trip per stage would otherwise pace the ring).  A lane owns rows lane, lane + 32, ... of the B tile
+// (<= 8 rows: tile_n <= 256); a stage holds <= 2 k-blocks (the host caps ks at 2 for this form).
+constexpr int kMaskRows = 8, kMaskSubs = 2;
+
+__device__ __forceinline__ void mask_fetch(const GemmShape& g, const DownArgs& a, const TileCoord& t, int kb, int lane,
+                                           uint2 (&bits)[kMaskRows * kMaskSubs]) {
+  const int n_sub = min(g.ks, t.kb_end - kb);
+#pragma unroll
+  for (int sub = 0; sub < kMaskSubs; ++sub)
+#pragma unroll
+    for (int r = 0; r < kMaskRows; ++r) {
+      const int j = lane + 32 * r;
+      const int grow = t.n_blk * g.tile_n + j;
+      uint2 v = make_uint2(0u, 0u);
+      if (sub < n_sub && j < g.tile_n && grow < a.d)     // (rows beyond d are zero-filled by the TMA anyway)
+        v = __ldg(reinterpret_cast<const uint2*>(a.mask_bits + ((static_cast<size_t>(grow) * a.h) >> 5)) + (kb + sub));
+      bits[sub * kMaskRows + r] = v;
+    }
+}
+
+__device__ __forceinline__ void mask_loop(uint8_t* smem, PipeBarriers* bars, const GemmShape& g, const DownArgs& a,
+                                          int rn, int rm, int lane) {
+  int s = 0;
+  uint32_t ph = 0;
+  TileCoord t, tn;
+  uint2 cur[kMaskRows * kMaskSubs], nxt[kMaskRows * kMaskSubs];
+  bool have = tile_at(g, 0, rn, rm, t);
+  if (have) mask_fetch(g, a, t, t.kb_begin, lane, cur);
+  for (int it = 0; have; ++it) {
+    const bool have_next_tile = tile_at(g, it + 1, rn, rm, tn);
+    for (int kb = t.kb_begin; kb < t.kb_end; kb += g.ks) {
+      // next stage's bit words: in flight while this stage is waited for and edited
+      const bool more = kb + g.ks < t.kb_end;
+      if (more)
+        mask_fetch(g, a, t, kb + g.ks, lane, nxt);
+      else if (have_next_tile)
+        mask_fetch(g, a, tn, tn.kb_begin, lane, nxt);
+      tc::mbar_wait(&bars->full[s], ph);
+      const uint32_t b_base = tc::smem_u32(smem + s * g.stage_bytes) + g.ks * kABytes;
+#pragma unroll
+      for (int sub = 0; sub < kMaskSubs; ++sub)
+#pragma unroll
+        for (int r = 0; r < kMaskRows; ++r) {
+          const int j = lane + 32 * r;
+          // 128-byte-swizzled K-major tile: 16-byte chunk c of row j sits at chunk (c ^ (j & 7))
+          const uint32_t row = b_base + static_cast<uint32_t>(sub * g.tile_n + j) * 128u;
+          const uint32_t sw = static_cast<uint32_t>(j & 7);
+          uint32_t w = cur[sub * kMaskRows + r].x;
+          while (w) {
+            const uint32_t b = static_cast<uint32_t>(__ffs(w) - 1);
+            w &= w - 1;
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(row + (((b >> 3) ^ sw) << 4) + ((b & 7u) << 1)), "h"(static_cast<unsigned short>(0)) : "memory");
+          }
+          w = cur[sub * kMaskRows + r].y;
+          while (w) {
+            const uint32_t b = 32u + static_cast<uint32_t>(__ffs(w) - 1);
+            w &= w - 1;
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(row + (((b >> 3) ^ sw) << 4) + ((b & 7u) << 1)), "h"(static_cast<unsigned short>(0)) : "memory");
+          }
+        }
+      tc::fence_proxy_async_smem();      // generic-proxy edits -> the tensor core's async-proxy reads
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&bars->masked[s]);
+#pragma unroll
+      for (int i = 0; i < kMaskRows * kMaskSubs; ++i) cur[i] = nxt[i];
+      if (++s == g.stages) {
+        s = 0;
+        ph ^= 1u;
+      }
+    }
+    have = have_next_tile;
+    t = tn;
+  }
+}
+
+template <int CH, bool PAIR, bool MASK = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 down_proj_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant__ CUtensorMap tmap_w2,
                  const GemmShape g, const DownArgs a) {
@@ -621,7 +706,9 @@ down_proj_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_consta
   if (warp == 0 || warp == 3) {
     producer_loop<PAIR>(&tmap_h, &tmap_w2, smem, bars, g, rn, rm, warp == 0);   // warp-converged; one elected lane issues
   } else if (warp == 1) {
-    if (!PAIR || rm == 0) mma_loop<PAIR>(smem, bars, g, tmem_base, rn, rm);   // pair: the leader CTA issues for both
+    if (!PAIR || rm == 0) mma_loop<PAIR, MASK>(smem, bars, g, tmem_base, rn, rm);   // pair: the leader CTA issues for both
+  } else if (warp == 2) {
+    if constexpr (MASK) mask_loop(smem, bars, g, a, rn, rm, lane);
   } else if (warp >= kEpiWarp0) {
     const int ew = warp - kEpiWarp0;
     const int q = warp & 3;
@@ -1048,9 +1135,29 @@ size_t moe_down_proj_workspace_bytes(int T, int h, int d) {
   return kCounterBytes + want;
 }
 
+static int down_proj_impl(const void* H, const void* w2p, const uint32_t* mask_bits, const float* b2, void* Y, int T, int h,
+                          int d, void* workspace, size_t workspace_bytes, void* stream);
+
 int moe_down_proj(const void* H, const void* w2p, const float* b2, void* Y, int T, int h, int d, void* workspace,
                   size_t workspace_bytes, void* stream) {
+  return down_proj_impl(H, w2p, nullptr, b2, Y, T, h, d, workspace, workspace_bytes, stream);
+}
+
+int moe_down_proj_masked(const void* H, const void* w2p, const uint32_t* mask_bits, const float* b2, void* Y, int T, int h,
+                         int d, void* workspace, size_t workspace_bytes, void* stream) {
   using namespace moe;
+  MOE_REQUIRE(mask_bits != nullptr, MOE_ERR_INVALID_ARGUMENT, "moe_down_proj_masked: mask_bits is NULL (use moe_down_proj)");
+  MOE_REQUIRE(h % 64 == 0, MOE_ERR_UNSUPPORTED_SHAPE,
+              "moe_down_proj_masked: h=%d must be a multiple of 64 (use moe_mask_weights + moe_down_proj)", h);
+  MOE_REQUIRE((reinterpret_cast<uintptr_t>(mask_bits) & 7) == 0, MOE_ERR_INVALID_ARGUMENT,
+              "moe_down_proj_masked: mask_bits must be 8-byte aligned");
+  return down_proj_impl(H, w2p, mask_bits, b2, Y, T, h, d, workspace, workspace_bytes, stream);
+}
+
+static int down_proj_impl(const void* H, const void* w2p, const uint32_t* mask_bits, const float* b2, void* Y, int T, int h,
+                          int d, void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace moe;
+  const bool masked = mask_bits != nullptr;
   MOE_REQUIRE(T >= 0 && h >= 8 && d >= 8, MOE_ERR_INVALID_ARGUMENT, "moe_down_proj: bad sizes T=%d h=%d d=%d", T, h, d);
   if (T == 0) return MOE_OK;   // empty tensors have no storage to point at
   MOE_REQUIRE(H && w2p && Y, MOE_ERR_INVALID_ARGUMENT, "moe_down_proj: NULL H / w2p / Y");
@@ -1067,8 +1174,9 @@ int moe_down_proj(const void* H, const void* w2p, const float* b2, void* Y, int 
   const int m_tiles = (T + kBlockM - 1) / kBlockM;
   const int sms = sm_count();
   ClusterChoice forced_cc = {1, 1};
-  const bool forced = env_cluster("MOE_K3_CLUSTER", forced_cc);
-  const bool pair = m_tiles >= 2 && pair_enabled() && !forced;
+  const bool forced = !masked && env_cluster("MOE_K3_CLUSTER", forced_cc);
+  // (weight-masked form: single CTAs -- each masker warp signals its own CTA's MMA thread, no cluster-scope arrive)
+  const bool pair = m_tiles >= 2 && pair_enabled() && !forced && !masked;
   const int units = pair ? sms / 2 : sms;
   const int m_units = pair ? (m_tiles + 1) / 2 : m_tiles;
   const int num_kb = (h + kBlockK - 1) / kBlockK;
@@ -1094,7 +1202,8 @@ int moe_down_proj(const void* H, const void* w2p, const float* b2, void* Y, int 
     for (int sp = 1; sp <= max_split; ++sp) {
       if (sp > 1 && num_kb / sp < 8) break;              // keep at least 8 k-blocks per slice
       int kb_per = (num_kb + sp - 1) / sp;
-      const int ks_c = pick_ks(h, kb_per, pair ? bn / 2 : bn, kEpiWarps * kBiasSmemPerWarp + 16, !forced);
+      int ks_c = pick_ks(h, kb_per, pair ? bn / 2 : bn, kEpiWarps * kBiasSmemPerWarp + 16, !forced);
+      if (masked && ks_c > kMaskSubs) ks_c = kMaskSubs;
       kb_per = (kb_per + ks_c - 1) / ks_c * ks_c;        // whole stages per slice
       if (sp > 1 && (sp - 1) * kb_per >= num_kb) continue;   // no empty slices
       const long long rounds = (tiles * sp + units - 1) / units;
@@ -1139,6 +1248,7 @@ int moe_down_proj(const void* H, const void* w2p, const float* b2, void* Y, int 
   g.split_k = best_split;
   g.kb_per_slice = (num_kb + best_split - 1) / best_split;
   g.ks = pick_ks(h, g.kb_per_slice, pair ? best / 2 : best, kEpiWarps * kBiasSmemPerWarp + 16, !forced);
+  if (masked && g.ks > kMaskSubs) g.ks = kMaskSubs;
   g.kb_per_slice = (g.kb_per_slice + g.ks - 1) / g.ks * g.ks;
   while (g.split_k > 1 && (g.split_k - 1) * g.kb_per_slice >= num_kb) --g.split_k;
   if (forced) {   // validate a forced multicast shape the same way the heuristic would
@@ -1167,10 +1277,15 @@ int moe_down_proj(const void* H, const void* w2p, const float* b2, void* Y, int 
   a.d = d;
   a.ws_counters = static_cast<int*>(workspace);
   a.ws_partial = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + kCounterBytes);
+  a.mask_bits = mask_bits;
+  a.h = h;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define MOE_LAUNCH_DOWN(CHV)                                                       \
-  rc = g.pair ? launch_clustered(down_proj_kernel<CHV, true>, g, st, th, tw, g, a)  \
-              : launch_clustered(down_proj_kernel<CHV, false>, g, st, th, tw, g, a)
+  if (masked) MOE_REQUIRE(g.cn == 1 && g.cm == 1 && !g.pair && g.tile_n <= 32 * kMaskRows && g.ks <= kMaskSubs,
+                          MOE_ERR_UNSUPPORTED_SHAPE, "moe_down_proj_masked: tile shape not supported");
+#define MOE_LAUNCH_DOWN(CHV)                                                                   \
+  rc = masked ? launch_clustered(down_proj_kernel<CHV, false, true>, g, st, th, tw, g, a)       \
+       : g.pair ? launch_clustered(down_proj_kernel<CHV, true>, g, st, th, tw, g, a)            \
+                : launch_clustered(down_proj_kernel<CHV, false>, g, st, th, tw, g, a)
   switch (ch) {
     case 32: MOE_LAUNCH_DOWN(32); break;
     case 20: MOE_LAUNCH_DOWN(20); break;

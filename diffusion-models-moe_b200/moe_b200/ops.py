@@ -117,8 +117,10 @@ def splitk_workspace(device, stream_ptr: int, nbytes: int) -> torch.Tensor:
     return ws
 
 
-def down_proj(H, w2p, b2, out=None):
-    """K3.  H bf16 [T, h]; w2p bf16 [d, h]; b2 f32 [d] or None -> Y bf16 [T, d]."""
+def down_proj(H, w2p, b2, out=None, mask_bits=None):
+    """K3.  H bf16 [T, h]; w2p bf16 [d, h]; b2 f32 [d] or None -> Y bf16 [T, d].
+    `mask_bits` (int32 [d*h/32], bit r*h + c set = weight removed): Y = H (W2 * (1 - M))^T + b2 in ONE launch, the
+    mask applied to the W2 tiles in shared memory (moe_down_proj_masked; h % 64 == 0)."""
     lib = _lib.load()
     T, h = H.shape
     d = w2p.shape[0]
@@ -126,12 +128,18 @@ def down_proj(H, w2p, b2, out=None):
     _need(w2p, torch.bfloat16, "w2p", (d, h))
     if b2 is not None:
         _need(b2, torch.float32, "b2", (d,))
+    if mask_bits is not None:
+        _need(mask_bits, torch.int32, "mask_bits", (d * h // 32,))
     Y = out if out is not None else torch.empty((T, d), dtype=torch.bfloat16, device=H.device)
     _need(Y, torch.bfloat16, "out", (T, d))
     with torch.cuda.device(H.device):
         st = _stream(H)
         ws = splitk_workspace(H.device, st, int(lib.moe_down_proj_workspace_bytes(T, h, d)))
-        rc = lib.moe_down_proj(_ptr(H), _ptr(w2p), _ptr(b2), _ptr(Y), T, h, d, _ptr(ws), ws.numel(), st)
+        if mask_bits is None:
+            rc = lib.moe_down_proj(_ptr(H), _ptr(w2p), _ptr(b2), _ptr(Y), T, h, d, _ptr(ws), ws.numel(), st)
+        else:
+            rc = lib.moe_down_proj_masked(_ptr(H), _ptr(w2p), _ptr(mask_bits), _ptr(b2), _ptr(Y), T, h, d, _ptr(ws),
+                                          ws.numel(), st)
     _lib.check(rc, "moe_down_proj")
     return Y
 

@@ -4,7 +4,9 @@
 y = x (W2 * (1 - M[t][layer]))^T + b2 with M in {0,1}^{d x h}.  The reference keeps dense int64
 masks on the host and ships one to the device on EVERY layer call (up to 52 MB), clones W2 and
 runs the down-projection twice.  Here every mask is bit-packed on the device once (d*h/8 bytes);
-per call `moe_mask_weights` writes the masked bf16 copy and `moe_down_proj` consumes it."""
+per call ONE launch (`moe_down_proj_masked`) applies the bits to the W2 tiles in shared memory on their way to the
+tensor core -- no masked copy of W2 is written (inner dimensions that are not a multiple of 64 use
+`moe_mask_weights` + `moe_down_proj`)."""
 import os
 import pickle
 
@@ -104,8 +106,11 @@ class WandaRemoveNeuronsFast(NeuronPredictivity):
         w2, b2 = self._weights(module)
         geglu_state = getattr(module, '_moe_column_perm', None)
         bits = self.mask_bits(self.timestep, self.layer, x.device, geglu_state)
-        w2m = ops.mask_weights(w2, bits)
-        y = ops.down_proj(as_tokens(x), w2m, b2)
+        if w2.shape[1] % 64 == 0:
+            # ONE launch: the mask is applied to the W2 tiles in shared memory, between the TMA and the tensor core
+            y = ops.down_proj(as_tokens(x), w2, b2, mask_bits=bits)
+        else:
+            y = ops.down_proj(as_tokens(x), ops.mask_weights(w2, bits), b2)
         if output is not None:
             assert y.shape[-1] == output.shape[-1], "Output shape should be same as hidden states"
         self.update_time_layer()

@@ -144,3 +144,36 @@ def test_grouped_down_projection_rejects_other_expert_sizes(lib):
     y = M.down_grouped(torch.zeros(0, 1024, dtype=torch.bfloat16, device=DEV), e,
                        torch.zeros(64, 1024, dtype=torch.bfloat16, device=DEV), None, 16, 64)
     assert y.shape == (0, 64)
+
+
+@pytest.mark.parametrize("Tn,h,d,density", [(96, 128, 32, 0.05), (100, 256, 64, 0.5), (256, 1280, 320, 0.025), (8192, 1280, 320, 0.116),
+                                             (2048, 2560, 640, 0.03), (512, 5120, 1280, 0.05), (128, 5120, 1280, 1.0), (33, 192, 48, 0.0)])
+def test_masked_down_projection_in_one_launch(lib, Tn, h, d, density):
+    """moe_down_proj_masked: the bit mask is applied to the W2 tiles in shared memory -- result
+    bit-identical to moe_mask_weights + moe_down_proj, one launch, and within 1e-2 of the fp32 reference
+    F.linear(x, W2 * (1 - M), b2) (remove_wanda_neurons_fast.py:72-77)."""
+    g = torch.Generator().manual_seed(Tn + h)
+    H = torch.randn(Tn, h, generator=g).to(DEV, torch.bfloat16)
+    w2 = (torch.randn(d, h, generator=g) / h ** 0.5).to(DEV, torch.bfloat16)
+    b2 = torch.randn(d, generator=g).to(DEV)
+    dense = (torch.rand(d, h, generator=g) < density).to(torch.uint8)
+    dense[0, :] = 1 if density > 0 else 0                      # a fully masked output row
+    bits = M.mask_pack(dense.to(DEV).contiguous())
+    want = M.down_proj(H, M.mask_weights(w2, bits), b2)
+    M.reset_launch_count()
+    got = M.down_proj(H, w2, b2, mask_bits=bits)
+    torch.cuda.synchronize()
+    assert M.launch_count() == 1
+    assert torch.equal(got, want)
+    ref = torch.nn.functional.linear(H.float().cpu(), w2.float().cpu() * (1 - dense.float()), b2.cpu())
+    assert rel_err(got.float().cpu(), ref) < OUT_REL_TOL
+    if density > 0:
+        assert torch.equal(got[:, 0].float().cpu(), b2[0].cpu().bfloat16().float().expand(Tn))     # only the bias is left
+
+
+def test_masked_down_projection_needs_h_multiple_of_64(lib):
+    H = torch.zeros(8, 96, dtype=torch.bfloat16, device=DEV)
+    w2 = torch.zeros(16, 96, dtype=torch.bfloat16, device=DEV)
+    bits = torch.zeros(16 * 96 // 32, dtype=torch.int32, device=DEV)
+    with pytest.raises(_lib.MoeLibraryError, match="code -2"):
+        M.down_proj(H, w2, None, mask_bits=bits)
