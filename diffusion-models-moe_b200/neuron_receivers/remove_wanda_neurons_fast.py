@@ -4,9 +4,15 @@
 y = x (W2 * (1 - M[t][layer]))^T + b2 with M in {0,1}^{d x h}.  The reference keeps dense int64
 masks on the host and ships one to the device on EVERY layer call (up to 52 MB), clones W2 and
 runs the down-projection twice.  Here every mask is bit-packed on the device once (d*h/8 bytes);
-per call ONE launch (`moe_down_proj_masked`) applies the bits to the W2 tiles in shared memory on their way to the
-tensor core -- no masked copy of W2 is written (inner dimensions that are not a multiple of 64 use
-`moe_mask_weights` + `moe_down_proj`)."""
+the masked bf16 weights of every (timestep, layer) are materialised ONCE (`moe_mask_weights`) and stay resident in HBM
+(99 MB per timestep for the SD-1.5 FFNs, 5 GB for T = 51 -- 180 GB of HBM make the per-call work of the reference
+unnecessary), so from the second prompt on a layer call is ONE launch, `moe_down_proj`, at the speed of the unmasked
+down-projection.  `mask_mode`:
+    'cache'  (default) resident masked weights, up to `cache_bytes`; cells beyond the budget fall back to 'copy'
+    'copy'   two launches per call: moe_mask_weights into a scratch copy, then moe_down_proj (+2.4 .. 6 us per call)
+    'fused'  one launch, no copy at all: moe_down_proj_masked applies the bits to the W2 tiles in shared memory
+             between the TMA and the tensor core (measured 2-8x slower than 'copy': one masker warp per CTA cannot
+             keep up with the tensor pipe, profiles/r02_wanda_masked_k3.log; kept for memory-constrained use)"""
 import os
 import pickle
 
@@ -31,7 +37,7 @@ def pack_weight_mask(mask, device, column_perm=None) -> torch.Tensor:
 
 class WandaRemoveNeuronsFast(NeuronPredictivity):
     def __init__(self, seed, path_expert_indx, T, n_layers, replace_fn=GEGLU, keep_nsfw=False, hook_module='unet',
-                 remove_timesteps=None, weights_shape=None, **kw):
+                 remove_timesteps=None, weights_shape=None, *, mask_mode='cache', cache_bytes=32 << 30, **kw):
         # remove_timesteps / weights_shape: passed by MultiConceptRemoverWanda and the benchmarks but
         # rejected by the reference ctor; accepted and ignored here.
         kw.setdefault('capture_gates', False)
@@ -45,8 +51,14 @@ class WandaRemoveNeuronsFast(NeuronPredictivity):
                     continue
                 with open(os.path.join(path_expert_indx, f'timestep_{i}_layer_{j}.pkl'), 'rb') as f:
                     self.expert_indices[i][j] = pickle.load(f)   # scipy CSR (modularity/wanda.py:168-173)
+        if mask_mode not in ('cache', 'copy', 'fused'):
+            raise ValueError("mask_mode must be 'cache', 'copy' or 'fused'")
+        self.mask_mode = mask_mode
+        self.cache_bytes = cache_bytes
         self._bits = {}
         self._w_cache = {}
+        self._masked = {}            # (t, l) -> (key, masked bf16 W2): resident masked weights
+        self._masked_bytes = 0
         self.timestep = 0
         self.layer = 0
         self.gates = []
@@ -71,10 +83,26 @@ class WandaRemoveNeuronsFast(NeuronPredictivity):
     def invalidate(self):
         self._bits = {}
         self._w_cache = {}
+        self._masked = {}
+        self._masked_bytes = 0
 
-    def remove_hooks(self, hooks):
-        super().remove_hooks(hooks)
-        self._w_cache = {}          # bf16 copies of fp16 / fp32 weights live for one observe_activation
+    def _masked_weight(self, t, l, w2, bits):
+        """Resident masked copy of W2 for cell (t, l); rebuilt when the weight or the bit words changed."""
+        key = (w2.data_ptr(), w2._version, bits.data_ptr(), bits._version)
+        hit = self._masked.get((t, l))
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        nbytes = w2.numel() * 2
+        if hit is not None:
+            out = hit[1]                                    # same cell, new mask (union remover): reuse the storage
+        elif self._masked_bytes + nbytes <= self.cache_bytes:
+            out = torch.empty_like(w2)
+            self._masked_bytes += nbytes
+        else:
+            return ops.mask_weights(w2, bits)               # over budget: scratch copy for this call only
+        ops.mask_weights(w2, bits, out=out)
+        self._masked[(t, l)] = (key, out)
+        return out
 
     def _weights(self, module):
         """bf16 W2 and f32 b2 of the hooked Linear: the parameters themselves when already in those types, else a
@@ -106,9 +134,10 @@ class WandaRemoveNeuronsFast(NeuronPredictivity):
         w2, b2 = self._weights(module)
         geglu_state = getattr(module, '_moe_column_perm', None)
         bits = self.mask_bits(self.timestep, self.layer, x.device, geglu_state)
-        if w2.shape[1] % 64 == 0:
-            # ONE launch: the mask is applied to the W2 tiles in shared memory, between the TMA and the tensor core
-            y = ops.down_proj(as_tokens(x), w2, b2, mask_bits=bits)
+        if self.mask_mode == 'fused' and w2.shape[1] % 64 == 0:
+            y = ops.down_proj(as_tokens(x), w2, b2, mask_bits=bits)       # mask applied in shared memory, no copy
+        elif self.mask_mode == 'cache':
+            y = ops.down_proj(as_tokens(x), self._masked_weight(self.timestep, self.layer, w2, bits), b2)
         else:
             y = ops.down_proj(as_tokens(x), ops.mask_weights(w2, bits), b2)
         if output is not None:

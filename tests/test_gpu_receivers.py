@@ -585,3 +585,44 @@ def test_wanda_artefacts_round_trip_on_a_permuted_model(lib, tmp_path):
     assert rel_err(out[0][0].float().cpu(), yo) < 1.5e-2        # stock (cuBLAS) GEGLU + native masked down-projection
     y_unmasked = O.down_proj(r16(v * gt), w2, layer["b2"])
     assert rel_err(out[0][0].float().cpu(), y_unmasked) > rel_err(out[0][0].float().cpu(), yo) * 2
+
+
+def test_wanda_mask_modes_agree_and_cache_makes_it_one_launch(lib, golden_dir, tmp_path):
+    """WandaRemoveNeuronsFast: 'cache' (resident masked weights), 'copy' (mask_weights + K3) and 'fused' (mask applied
+    in shared memory) give the same bits; from the second prompt on 'cache' is ONE launch per layer call."""
+    import moe_b200 as M
+    import scipy.sparse as sp
+    g = load(golden_dir, "wanda_csv_320_1280")
+    d, h = 320, 1280
+    rs = np.random.RandomState(0)
+    mask = (rs.rand(d, h) < 0.03).astype(np.int64)
+    for t in range(2):
+        with open(tmp_path / f"timestep_{t}_layer_0.pkl", "wb") as f:
+            pickle.dump(sp.csr_matrix(mask if t == 0 else 1 - mask), f)
+    ff = FeedForward(d).to(DEV, torch.bfloat16)
+    pipe = _OnePipe(ff)
+    x = torch.randn(2, 200, d, device=DEV, dtype=torch.bfloat16)
+    outs = {}
+    for mode in ("cache", "copy", "fused"):
+        wr = nr.WandaRemoveNeuronsFast(0, str(tmp_path), 2, 1, mask_mode=mode)
+        out, _ = wr.observe_activation(pipe, [x, x])
+        outs[mode] = [o.clone() for o in out[0]]
+        wr.reset_time_layer()
+        M.reset_launch_count()
+        out2, _ = wr.observe_activation(pipe, [x, x])
+        torch.cuda.synchronize()
+        assert M.launch_count() == {"cache": 2, "copy": 4, "fused": 2}[mode]
+        assert all(torch.equal(a, b) for a, b in zip(outs[mode], out2[0]))
+    for mode in ("copy", "fused"):
+        assert all(torch.equal(a, b) for a, b in zip(outs["cache"], outs[mode]))
+    Hd = ff.net[0](x).float().cpu()
+    ref0 = torch.nn.functional.linear(r16(Hd), ff.net[2].weight.float().cpu() * torch.from_numpy(1 - mask).float(), ff.net[2].bias.float().cpu())
+    assert rel_err(outs["cache"][0].float().cpu(), ref0) < 1.5e-2
+    # an in-place weight update invalidates the resident copy
+    wr = nr.WandaRemoveNeuronsFast(0, str(tmp_path), 2, 1)
+    a, _ = wr.observe_activation(pipe, [x])
+    with torch.no_grad():
+        ff.net[2].weight.mul_(2.0)
+    wr.reset_time_layer()
+    b, _ = wr.observe_activation(pipe, [x])
+    assert rel_err(b[0][0].float() - ff.net[2].bias.float(), 2 * (a[0][0].float() - ff.net[2].bias.float())) < 2e-2
