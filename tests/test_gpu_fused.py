@@ -56,6 +56,50 @@ def test_fused_config1_full_size_matches_unfused_and_oracle(lib):
     assert int(fu["hist"].sum()) == 4096 * 19
 
 
+@pytest.mark.parametrize("d,h,shape,es", [(640, 2560, (2, 1024), 20), (1280, 5120, (2, 256), 20), (320, 1280, (2, 4096), 64),
+                                          (1280, 5120, (2, 64), 64)])
+def test_fused_full_size_layers_match_oracle(lib, d, h, shape, es):
+    """The other SD-1.5 layer shapes of BASELINE configs[1] at FULL size against the oracle (not against the separate
+    kernels): d = 640 / 2048 tokens, d = 1280 / 512 tokens (split-K down-projection), and the BASELINE-literal
+    64-neuron experts at 8192 tokens and at the mid-block's 128 tokens."""
+    layer = O.synthetic_layer(d, h, shape, es, seed=d + shape[1])
+    fu = fused_layer(layer, 0.3)
+    orc = oracle_layer(layer, 0.3)
+    stats = check_layer(fu, orc, min_safe_fraction=0.85)
+    assert int(fu["hist"].sum()) == shape[1] * fu["k"]
+    print(stats)
+
+
+def test_fused_kernel_finishes_next_to_a_competing_kernel(lib):
+    """the fused kernel's CTA pairs wait on each other, so a kernel of another stream that holds
+    SMs delays the pairs that found none -- it must finish (the stragglers start when the competitor's CTAs retire),
+    not trap, and give the same bits as an undisturbed launch.  Two fused launches on two streams are ordered by the
+    library (they must never be resident together)."""
+    layer = O.synthetic_layer(320, 1280, (2, 2048), 20, seed=9)
+    ref = fused_layer(layer, 0.3)
+    from moe_b200.packing import ExpertLayout, pack_ffn
+    lay = ExpertLayout.from_labels(layer["labels"])
+    E, es, k = lay.n_experts, lay.expert_size, ref["k"]
+    p = pack_ffn(lay, layer["w1"], layer["b1"], layer["w2"], layer["b2"], device=DEV)
+    xt = layer["x"].reshape(-1, 320).to(DEV, torch.bfloat16).contiguous()
+    side, side2 = torch.cuda.Stream(), torch.cuda.Stream()
+    big = torch.randn(8192, 8192, device=DEV, dtype=torch.bfloat16)
+    torch.cuda.synchronize()
+    outs = []
+    for rep in range(3):
+        with torch.cuda.stream(side):                      # ~2 ms of cuBLAS work occupying the SMs
+            for _ in range(3):
+                big @ big
+        y, _, _, bits, _ = M.ffn_fused(xt, p.w1p, p.b1p, p.w2p, p.b2, E, es, k, want_bits=True)    # current stream
+        with torch.cuda.stream(side2):                     # a second fused launch on another stream
+            y2, _, _, bits2, _ = M.ffn_fused(xt, p.w1p, p.b1p, p.w2p, p.b2, E, es, k, want_bits=True)
+        outs.append((y, bits, y2, bits2))
+    torch.cuda.synchronize()
+    for y, bits, y2, bits2 in outs:
+        assert torch.equal(bits.cpu(), ref["bits"]) and torch.equal(bits2.cpu(), ref["bits"])
+        assert torch.equal(y.float().cpu().view(ref["y"].shape), ref["y"]) and torch.equal(y2.float().cpu().view(ref["y"].shape), ref["y"])
+
+
 def test_fused_removed_experts_and_count_window(lib):
     """RemoveExperts rule inside the fused kernel: removed experts score exactly 0, still compete, own no neurons
     (remove_skilled_experts.py:29-49); the histogram counts the rows of the given window only."""
