@@ -160,29 +160,46 @@ __device__ __forceinline__ void route_chunk(const G& g, const A& a, int tok0, in
     uint32_t srt[KPT];
 #pragma unroll
     for (int r = 0; r < KPT; ++r) srt[r] = key[r];
-    // sizes up to KPT: entirely inside the lane, directions known at compile time except for size == KPT ... N
+    // Bitonic sort in the "flip" formulation: every compare-exchange keeps the minimum at the LOWER element index, so
+    // there are no direction selects (the classic formulation costs two SELs per compare-exchange).  Merging blocks of
+    // size k: first compare element i with its mirror image i ^ (k - 1) inside the block, then with i ^ j for
+    // j = k / 4 ... 1.  Distances below KPT stay inside the lane (compile-time register pairs, min / max only);
+    // beyond, the partner lane is part ^ mask and, for the mirror step, the register index is reversed.
 #pragma unroll
-    for (int size = 2; size <= KPT; size <<= 1) {
-      const bool lane_up = ((part * KPT) & size) == 0;   // only matters for size == KPT's parent bit: (i & size)
+    for (int k2 = 2; k2 <= KPT; k2 <<= 1) {
 #pragma unroll
-      for (int stride = size >> 1; stride >= 1; stride >>= 1) {
+      for (int r = 0; r < KPT; ++r) {          // mirror step inside the lane
+        const int q = r ^ (k2 - 1);
+        if (r < q) {
+          const uint32_t lo = min(srt[r], srt[q]), hi = max(srt[r], srt[q]);
+          srt[r] = lo;
+          srt[q] = hi;
+        }
+      }
+#pragma unroll
+      for (int j = k2 >> 2; j >= 1; j >>= 1) {
 #pragma unroll
         for (int r = 0; r < KPT; ++r) {
-          if ((r & stride) == 0) {
-            const bool up = (size < KPT) ? ((r & size) == 0) : lane_up;
-            const uint32_t lo = min(srt[r], srt[r | stride]), hi = max(srt[r], srt[r | stride]);
-            srt[r] = up ? lo : hi;
-            srt[r | stride] = up ? hi : lo;
+          if ((r & j) == 0) {
+            const uint32_t lo = min(srt[r], srt[r | j]), hi = max(srt[r], srt[r | j]);
+            srt[r] = lo;
+            srt[r | j] = hi;
           }
         }
       }
     }
-    // sizes beyond one lane: lane distances L' = size / KPT / 2 ... 1 through shuffles, then the in-lane strides
-    for (int lsize = 2; lsize <= L; lsize <<= 1) {        // size = lsize * KPT
-      const bool up = (part & lsize) == 0 || lsize == L;   // the last merge sorts everything ascending
-      for (int ls = lsize >> 1; ls >= 1; ls >>= 1) {
-        const bool lower = (part & ls) == 0;
-        const bool keep_min = lower == up;
+    for (int lsize = 2; lsize <= L; lsize <<= 1) {        // blocks of k = lsize * KPT elements
+      {
+        // mirror step: lane part ^ (lsize - 1), register KPT - 1 - r; the lane with the lower index keeps the minima
+        const bool keep_min = (part & (lsize >> 1)) == 0;
+        uint32_t other[KPT];
+#pragma unroll
+        for (int r = 0; r < KPT; ++r) other[r] = __shfl_xor_sync(full, srt[KPT - 1 - r], lsize - 1);
+#pragma unroll
+        for (int r = 0; r < KPT; ++r) srt[r] = keep_min ? min(srt[r], other[r]) : max(srt[r], other[r]);
+      }
+      for (int ls = lsize >> 2; ls >= 1; ls >>= 1) {
+        const bool keep_min = (part & ls) == 0;
 #pragma unroll
         for (int r = 0; r < KPT; ++r) {
           const uint32_t other = __shfl_xor_sync(full, srt[r], ls);
@@ -190,13 +207,13 @@ __device__ __forceinline__ void route_chunk(const G& g, const A& a, int tok0, in
         }
       }
 #pragma unroll
-      for (int stride = KPT >> 1; stride >= 1; stride >>= 1) {
+      for (int j = KPT >> 1; j >= 1; j >>= 1) {
 #pragma unroll
         for (int r = 0; r < KPT; ++r) {
-          if ((r & stride) == 0) {
-            const uint32_t lo = min(srt[r], srt[r | stride]), hi = max(srt[r], srt[r | stride]);
-            srt[r] = up ? lo : hi;
-            srt[r | stride] = up ? hi : lo;
+          if ((r & j) == 0) {
+            const uint32_t lo = min(srt[r], srt[r | j]), hi = max(srt[r], srt[r | j]);
+            srt[r] = lo;
+            srt[r | j] = hi;
           }
         }
       }
@@ -283,6 +300,10 @@ __device__ __forceinline__ void route_chunk(const G& g, const A& a, int tok0, in
     // materialise the masked hidden state: zero the neurons of every expert outside the token's active set
     // (write-only; 16-byte units, 4-neuron groups never straddle an expert because es % 4 == 0)
     const int units = g.h >> 3;
+    // (A variant that kept the tokens' expert words in registers and hoisted the two divisions per unit out of the
+    // token loop was measured 1.5 % SLOWER end to end: this stage is paced by the 7 TB/s of zero stores into L2, not
+    // by its instructions -- profiles/r02_route_ab.log.)
+    {
     for (int tt = 0; tt < tpw; ++tt) {
       const int tok = tok0 + tpw * ew + tt;
       if (tok >= tok_end) break;
@@ -300,6 +321,7 @@ __device__ __forceinline__ void route_chunk(const G& g, const A& a, int tok0, in
         if (!on_a) half[0] = make_uint2(0u, 0u);
         if (!on_b) half[1] = make_uint2(0u, 0u);
       }
+    }
     }
   }
   __syncwarp();
