@@ -142,6 +142,7 @@ struct Shape {
   int words;                                    // expert-set words per token
   int act, mask_h, count_begin, count_end;
   int prefetch_weights;
+  int pub_batch;                                // phase-1 tiles published per GPU-scope release (2 .. 4)
   uint32_t es_magic;
 };
 
@@ -797,7 +798,14 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       // column groups are combined here from shared-memory partial sums.
       int st_it = 0;
       int use_p1[2] = {0, 0};
-      int pending_blk = -1, prev_blk = -1;
+      // Publication of finished tiles (done[m] += 1) is BATCHED: a GPU-scope release costs ~1 us (MEMBAR.ALL.GPU waits
+      // for every outstanding store of the SM), and paid once per tile it made this warp the pacemaker of phase 1
+      // (2.5 - 2.7 us per tile against 2.2 us of tensor work at UNet batch 16: the in-kernel timeline showed the
+      // "stored + signalled" stamps falling 0.4 us further behind with every tile).  Nobody consumes done[m] before
+      // the block's LAST tile is in, so up to g.pub_batch - 1 finished tiles wait for one common fence.
+      constexpr int kPubBatch = 8;
+      int pend[kPubBatch] = {-1, -1, -1, -1, -1, -1, -1, -1};
+      int n_pend = 0;
       Item t;
       for (int it = 0; item1(g, it, p, P, rm, t); ++it, ++st_it) {
         const int buf = st_it & 1;
@@ -837,38 +845,41 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           if (it >= 2 && it < 4) TRACE(41 + 4 * (it - 2));
 #endif
           Item nx;
-          prev_blk = -1;
-          if (pending_blk >= 0 && !item1(g, it + 1, p, P, rm, nx)) {
-            prev_blk = pending_blk;         // last tile: its predecessor is published together with it, after the loop
-          } else if (pending_blk >= 0) {
-            tc::tma_store_wait<1>();        // every group but the one just committed is globally written
+          if (n_pend >= g.pub_batch - 1 && item1(g, it + 1, p, P, rm, nx)) {
+            // the batch is full (and this is not the pair's last tile, whose publication follows the loop): every store
+            // group but the one just committed is globally written -- one fence, then the counts
+            tc::tma_store_wait<1>();
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
+#pragma unroll
+            for (int i = 0; i < kPubBatch - 1; ++i)
+              if (i < n_pend) atomicAdd(ws_rec + pend[i] * kBlockRecInts, 1);
+            n_pend = 0;
 #if MOE_TRACE
             if (it >= 2 && it < 4) TRACE(42 + 4 * (it - 2));
-#endif
-            red_release_add(ws_rec + pending_blk * kBlockRecInts, 1);   // previous H tile + its scores, then the count
-#if MOE_TRACE
             if (st_it - 1 < 13) TRACE(8 + 4 * (st_it - 1) + 3);
             if (it >= 2 && it < 4) TRACE(43 + 4 * (it - 2));
 #endif
           }
+#pragma unroll
+          for (int i = 0; i < kPubBatch; ++i)
+            if (i == n_pend) pend[i] = t.m_blk;
+          ++n_pend;
         }
-        pending_blk = t.m_blk;
         ++use_p1[buf];
         __syncwarp();
       }
-      if (pending_blk >= 0) {
-        __syncwarp();   // (span mode: the lanes' score stores above are already fenced)
-        if (lane == 0) {
-          // the critical path of the phase: one wait for the outstanding stores, ONE release fence, then the counts
-          // of the last tile and (if it was deferred) of its predecessor
-          tc::tma_store_wait<0>();
-          asm volatile("fence.acq_rel.gpu;" ::: "memory");
-          if (prev_blk >= 0) atomicAdd(ws_rec + prev_blk * kBlockRecInts, 1);
-          atomicAdd(ws_rec + pending_blk * kBlockRecInts, 1);
+      __syncwarp();   // (span mode: the lanes' score stores above are already fenced)
+      if (lane == 0 && n_pend > 0) {
+        // the critical path of the phase: one wait for the outstanding stores, ONE release fence, then the counts of
+        // the pair's last (up to kPubBatch) tiles
+        tc::tma_store_wait<0>();
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < kPubBatch; ++i)
+          if (i < n_pend) atomicAdd(ws_rec + pend[i] * kBlockRecInts, 1);
 #if MOE_TRACE
-          if (st_it - 1 < 13) TRACE(8 + 4 * (st_it - 1) + 3);
+        if (st_it - 1 < 13) TRACE(8 + 4 * (st_it - 1) + 3);
 #endif
-        }
       }
       __syncwarp();
     }
@@ -881,20 +892,28 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       uint32_t r_posted = 0;
       Item t;
       const int consumers = g.n_tiles3 * g.split3;      // phase-3 items per row block
-      for (int it = 0; item3(g, it, p, P, rm, t); ++it) {
-        // wait until every phase-1 tile of the block is published, then route this item's share of the block:
-        // consumer r of the block's `consumers` items takes chunks r, r + consumers, ...
-        poll_at_least(ws_rec + t.m_blk * kBlockRecInts, g.n_tiles1);
-        // the epilogue warps route this item's chunks (same formula there); count them for the block's consumers
+      // Routing hand-shake of ONE phase-3 item: wait until every phase-1 tile of its block is published, let the
+      // epilogue warps route this item's share of the block (consumer r of the block's `consumers` items takes chunks
+      // r, r + consumers, ...), then count the share for the block's consumers.  It runs ONE ITEM AHEAD of the item's
+      // tensor work: while the MMA thread is in item i's main loop the epilogue warps route item i + 1, so with several
+      // items per pair (UNet batch 16: seven) a pair no longer alternates 6 us of routing with 6 us of MMAs.  (An item
+      // waits only for phase-1 tiles and for the routing of its own block, so routing ahead cannot deadlock.)
+      auto handshake = [&](const Item& ti) {
+        poll_at_least(ws_rec + ti.m_blk * kBlockRecInts, g.n_tiles1);
         tc::mbar_arrive(&bars->route_req);
         tc::mbar_wait(&bars->route_done, r_posted & 1u);
         ++r_posted;
         int mine = 0;
-        for (int c = t.n * g.split3 + t.slice; c < g.chunks_per_block; c += consumers) ++mine;
+        for (int c = ti.n * g.split3 + ti.slice; c < g.chunks_per_block; c += consumers) ++mine;
         // release at GPU scope: the epilogue threads' labels / zero-writes were ordered before route_done (mbarrier
         // arrive = release.cta, wait = acquire.cta), the release is cumulative over them
-        if (mine > 0) red_release_add(ws_rec + t.m_blk * kBlockRecInts + 1, mine);
-        block_consumed(ws_rec + t.m_blk * kBlockRecInts, 2 * consumers);
+        if (mine > 0) red_release_add(ws_rec + ti.m_blk * kBlockRecInts + 1, mine);
+        block_consumed(ws_rec + ti.m_blk * kBlockRecInts, 2 * consumers);
+      };
+      if (item3(g, 0, p, P, rm, t)) handshake(t);
+      for (int it = 0; item3(g, it, p, P, rm, t); ++it) {
+        Item nx;
+        if (item3(g, it + 1, p, P, rm, nx)) handshake(nx);
         if (g.split3 == 1) {
           tc::mbar_wait(&bars->hs_full[0], use[0] & 1u);
           {   // clipped at T rows / d columns
@@ -1042,22 +1061,29 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     {
       const int cpg = g.bn / 4;
       const int col0 = cg * cpg;
-      for (int it = 0; item3(g, it, p, P, rm, t); ++it, ++acc_it) {
-        const int as = acc_it & 1;
-        // ---- routing role: once the sync warp has seen every phase-1 tile of the block, route this item's share
-        // of the block's chunks (consumer r of the block's items takes chunks r, r + consumers, ...)
-        tc::mbar_wait(&bars->route_req, it & 1u);
+      // ---- routing role, one item ahead of the item's epilogue (see the sync warp): once the sync warp has seen every
+      // phase-1 tile of the block, route this item's share of the block's chunks
+      auto route_item = [&](const Item& ti, int idx) {
+        tc::mbar_wait(&bars->route_req, idx & 1u);
 #if MOE_TRACE
-        if (ew == 0 && lane == 0 && it == 0) TRACE(60);
+        if (ew == 0 && lane == 0 && idx == 0) TRACE(60);
 #endif
-        for (int c = t.n * g.split3 + t.slice; c < g.chunks_per_block; c += g.n_tiles3 * g.split3)
-          route_dispatch(g, a, t.m_blk * kBlockM + c * g.chunk_tokens, min(g.T, (t.m_blk + 1) * kBlockM), ew, lane, s_words,
+        for (int c = ti.n * g.split3 + ti.slice; c < g.chunks_per_block; c += g.n_tiles3 * g.split3)
+          route_dispatch(g, a, ti.m_blk * kBlockM + c * g.chunk_tokens, min(g.T, (ti.m_blk + 1) * kBlockM), ew, lane, s_words,
                          s_hist);
         __syncwarp();        // every lane's zero-writes / labels before lane 0's arrive (release at CTA scope; the sync
         if (lane == 0) tc::mbar_arrive(&bars->route_done);   // warp's red.release then publishes them device-wide)
 #if MOE_TRACE
         if (ew == 0 && lane == 0) TRACE(61);
 #endif
+      };
+      if (item3(g, 0, p, P, rm, t)) route_item(t, 0);
+      for (int it = 0; item3(g, it, p, P, rm, t); ++it, ++acc_it) {
+        const int as = acc_it & 1;
+        {
+          Item nx;
+          if (item3(g, it + 1, p, P, rm, nx)) route_item(nx, it + 1);
+        }
         const int n0 = t.n * g.bn + col0;                  // first output column of this warp's group
         const int nvalid = max(0, min(cpg, g.d - n0));     // the last tile may overhang d
         stage_bias(sbias, a.b2 != nullptr ? a.b2 + n0 : nullptr, nullptr, nvalid, lane);
@@ -1576,6 +1602,13 @@ int moe_ffn_fused(const void* x, const void* w1p, const float* b1p, const void* 
   g.es_magic = static_cast<uint32_t>((0x100000000ull / static_cast<unsigned>(es)) + 1ull);
   g.prefetch_weights = 1;
   if (const char* e = getenv("MOE_FUSED_PREFETCH")) g.prefetch_weights = atoi(e) != 0;
+  // tiles published per release: pairs with few tiles publish each one (early finishers start routing the early blocks),
+  // pairs with many amortise the fence (measured: profiles/r02_sweep_publication_batch.log)
+  g.pub_batch = (g.items1 >= 6 * P) ? 4 : 2;
+  if (const char* e = getenv("MOE_FUSED_PUB")) {
+    const int v = atoi(e);
+    if (v >= 2 && v <= 8) g.pub_batch = v;
+  }
 
   if (getenv("MOE_DEBUG_PRINT"))
     fprintf(stderr,
