@@ -54,6 +54,7 @@ SIGNATURES = {
                                      c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, ctypes.c_size_t, c_void_p]),
     "moe_down_grouped": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                  c_int, c_int, c_int, c_void_p, ctypes.c_size_t, c_void_p]),
+    "moe_cfg_ddim_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_float, c_float, c_float, c_void_p]),
     "moe_down_grouped_rows": (ctypes.c_size_t, [c_int, c_int, c_int]),
     "moe_down_grouped_workspace_bytes": (ctypes.c_size_t, [c_int, c_int, c_int, c_int]),
 }

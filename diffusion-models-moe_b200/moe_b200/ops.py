@@ -390,3 +390,21 @@ def mask_weights(w2, bits, out=None):
         rc = lib.moe_mask_weights(_ptr(w2), _ptr(bits), _ptr(out), d, h, _stream(w2))
     _lib.check(rc, "moe_mask_weights")
     return out
+
+
+def cfg_ddim_step(eps_uncond, eps_cond, x, guidance: float, alpha_t: float, alpha_prev: float, out=None):
+    """Classifier-free-guidance combine + DDIM (eta = 0) update in one kernel (moe_cfg_ddim_step).  f32 or bf16 tensors
+    of equal shape; alpha_* are the scheduler's cumulative alpha products at this / the previous timestep."""
+    lib = _lib.load()
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        raise ValueError("cfg_ddim_step: f32 or bf16 latents only")
+    for name, t in (("eps_uncond", eps_uncond), ("eps_cond", eps_cond), ("x", x)):
+        _need(t, x.dtype, name, x.shape)
+    if out is None:
+        out = torch.empty_like(x)
+    _need(out, x.dtype, "out", x.shape)
+    with torch.cuda.device(x.device):
+        rc = lib.moe_cfg_ddim_step(_ptr(eps_uncond), _ptr(eps_cond), _ptr(x), _ptr(out), x.numel(), 1 if x.dtype == torch.bfloat16 else 0,
+                                   float(guidance), float(alpha_t), float(alpha_prev), _stream(x))
+    _lib.check(rc, "moe_cfg_ddim_step")
+    return out

@@ -216,6 +216,14 @@ MOE_API int moe_wanda_score_mask(const void* w2, const float* norm_base, const f
  * benchmarks/save_union_over_time.py:192-205 (sum of T CSR masks > select_ratio * T).  masks u32 [T][n_words]. */
 MOE_API int moe_mask_vote(const uint32_t* masks, int T, long long n_words, float threshold, uint32_t* out, void* stream);
 
+/* The sampler step around the UNet call, one streaming kernel: classifier-free-guidance combine
+ * and DDIM (eta = 0) update, x_prev = sqrt(a_prev) x0 + sqrt(1 - a_prev) eps with eps = eps_u + guidance (eps_c - eps_u)
+ * and x0 = (x - sqrt(1 - a_t) eps) / sqrt(a_t).  Replaces the chain of elementwise ATen kernels of the stock pipeline
+ * [upstream StableDiffusionPipeline.__call__ + DDIMScheduler.step, driven by base_receiver.py:73].  All four tensors
+ * have n elements, f32 (is_bf16 = 0) or bf16 (is_bf16 = 1); x_prev may alias x.  alpha_* = cumulative alpha products. */
+MOE_API int moe_cfg_ddim_step(const void* eps_uncond, const void* eps_cond, const void* x, void* x_prev, long long n,
+                    int is_bf16, float guidance, float alpha_t, float alpha_prev, void* stream);
+
 /*
  * Fused layer call -- the whole MoEfied GEGLU FFN of one BasicTransformerBlock in ONE persistent kernel:
  * up-projection + activation + product + expert scores (as moe_geglu_up), per-token top-k routing with the

@@ -177,3 +177,21 @@ def test_masked_down_projection_needs_h_multiple_of_64(lib):
     bits = torch.zeros(16 * 96 // 32, dtype=torch.int32, device=DEV)
     with pytest.raises(_lib.MoeLibraryError, match="code -2"):
         M.down_proj(H, w2, None, mask_bits=bits)
+
+
+@pytest.mark.parametrize("dtype,n", [(torch.float32, 2 * 4 * 64 * 64), (torch.bfloat16, 16 * 4 * 64 * 64), (torch.float32, 1003),
+                                      (torch.bfloat16, 7)])
+def test_cfg_ddim_step_matches_torch(lib, dtype, n):
+    """CFG combine + DDIM update in one kernel against the formula in fp32 torch."""
+    g = torch.Generator().manual_seed(n)
+    eu, ec, x = (torch.randn(n, generator=g).to(DEV, dtype) for _ in range(3))
+    guidance, a_t, a_prev = 7.5, 0.37, 0.52
+    got = M.cfg_ddim_step(eu, ec, x, guidance, a_t, a_prev)
+    fe, fc, fx = eu.float(), ec.float(), x.float()
+    eps = fe + guidance * (fc - fe)
+    x0 = (fx - (1 - a_t) ** 0.5 * eps) / a_t ** 0.5
+    want = a_prev ** 0.5 * x0 + (1 - a_prev) ** 0.5 * eps
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    assert got.dtype == dtype and rel_err(got.float(), want) < tol
+    M.cfg_ddim_step(eu, ec, x, guidance, a_t, a_prev, out=x)           # in place
+    assert torch.equal(x, got)

@@ -320,3 +320,35 @@ def test_fused_down_projection_patch_is_undone():
     assert all("forward" not in d.__dict__ for d in downs)           # CPU weights: the reference flow is kept
     rec.remove_hooks(hooks)
     assert rec._fused_states == [] and all(not m._moe_state.fused_down for m in unet.modules() if isinstance(m, GEGLU))
+
+
+def test_balanced_kmeans_split_meets_the_reference_contract(tmp_path):
+    """SURVEY 8f row 4 (moe_utils.py:97-107): equally sized experts from the gate half of W1, saved in the reference's
+    label-file format and consumed by helper.modify_ffn_to_experts."""
+    from moefication import moe_utils
+    torch.manual_seed(0)
+    unet = _tiny_unet()
+    # plant structure: 8 groups of 16 gate rows around 8 directions, shuffled -> the split must find the groups
+    g0 = unet.transformer_blocks[0].ff.net[0]
+    dirs = torch.nn.functional.normalize(torch.randn(8, 32), dim=1)
+    perm = torch.randperm(128)
+    with torch.no_grad():
+        g0.proj.weight[128:][perm] = (dirs.repeat_interleave(16, 0) + 0.05 * torch.randn(128, 32))
+    labels = moe_utils.split_ffn_weight(g0.proj.weight, 16, seed=0)
+    assert len(labels) == 128 and np.bincount(labels).tolist() == [16] * 8
+    assert labels == moe_utils.split_ffn_weight(g0.proj.weight, 16, seed=0)                 # deterministic
+    planted = torch.empty(128, dtype=torch.long)
+    planted[perm] = torch.arange(8).repeat_interleave(16)
+    for e in range(8):                                          # every expert is exactly one planted group
+        assert len(set(planted[[i for i, l in enumerate(labels) if l == e]].tolist())) == 1
+    rnd = [i // 16 for i in range(128)]
+    assert moe_utils.inertia(g0.proj.weight[128:], labels) < 0.2 * moe_utils.inertia(g0.proj.weight[128:], rnd)
+    with pytest.raises(ValueError, match="divisible"):
+        moe_utils.balanced_kmeans(torch.randn(30, 4), 8)
+    # whole-model driver -> label files -> the reference's loading path
+    args = _Args()
+    args.res_path = str(tmp_path)
+    written = moe_utils.moefy_sd_model(_Pipe(unet), str(tmp_path), expert_size=16 if False else 8)
+    assert sorted(written) == sorted(n + ".proj.weight" for n, m in unet.named_modules() if isinstance(m, GEGLU))
+    _, names, n_exp = helper.modify_ffn_to_experts(_Pipe(unet), args)
+    assert list(n_exp.values()) == [16, 20] and unet.transformer_blocks[0].ff.net[0].expert_size == 8
