@@ -79,7 +79,7 @@ constexpr int kEpiWarp0 = 4;
 constexpr int kEpiWarps = 16;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kNumThreads = kEpiWarp0 * 32 + kEpiThreads;
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 12;
 constexpr int kSmemLimit = 232448;
 constexpr int kBiasBytesPerWarp = 128 * 4;          // 2 x 64 floats
 constexpr int kSpartPerRow = 8;                      // partial / per-expert score slots per token row and tile
@@ -128,6 +128,7 @@ struct Shape {
   // buffers' space becomes a fourth ring slot for the phase whose main loop is bound by k-blocks in flight
   int sep_ring1, ring1_off, direct_h;
   int tail_off, spart_bytes;                    // small per-warp arrays + barriers start at tail_off
+  int hs_off;                                   // the two staging buffers start here (after the operand ring area)
   int experts_per_tile, chunks_per_expert, span;
   // phase 3
   int bn, n_tiles3, ks3, nkb3, split3, kb_per_slice3, items3;
@@ -337,6 +338,30 @@ __device__ __forceinline__ bool item3(const Shape& g, int it, int p, int P, int 
 using route::route_chunk;
 using route::route_dispatch;
 
+// phase-1 tiles of a pair without divisions in the loop (the MMA warp walks its list on the critical path of every
+// tile: item1() costs ~0.4 us of integer divisions per call)
+struct Tile1Iter {
+  int i, end, stride, mp, n, n_tiles1, step_m, step_n;
+  __device__ __forceinline__ void init(const Shape& g, int p, int P) {
+    range1(g, p, P, i, end, stride);
+    n_tiles1 = g.n_tiles1;
+    step_m = g.step_m1;
+    step_n = g.step_n1;
+    mp = i / n_tiles1;
+    n = i - mp * n_tiles1;
+  }
+  __device__ __forceinline__ bool valid() const { return i < end; }
+  __device__ __forceinline__ void next() {
+    i += stride;
+    mp += step_m;
+    n += step_n;
+    if (n >= n_tiles1) {
+      n -= n_tiles1;
+      ++mp;
+    }
+  }
+};
+
 // ------------------------------------------------------------------------------------------ the kernel
 // per-warp bias slices staged in shared memory: lanes load coalesced, everyone re-reads float4 broadcasts
 __device__ __forceinline__ void stage_bias(float* sb, const float* b0, const float* b1, int n, int lane) {
@@ -526,7 +551,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) TRACE(0);
   uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* hstage = smem + g.stages * g.slot_bytes;
+  uint8_t* hstage = smem + g.hs_off;
   float* sbias_all = reinterpret_cast<float*>(smem + g.tail_off);
   float* spart = sbias_all + kEpiWarps * (kBiasBytesPerWarp / 4);             // [2][128][kSpartPerRow], or empty
   uint32_t* s_words_all = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(spart) + g.spart_bytes);   // [16 warps][16]: tokens per warp x words
@@ -721,7 +746,24 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           ph = 0;
         }
         int cur_mp = -1, a_runs = 0;
-        for (int it = 0; phase == 0 ? item1(g, it, p, P, rm, t) : item3(g, it, p, P, rm, t); ++it, ++acc_it) {
+        Tile1Iter it1;
+        it1.init(g, p, P);
+        for (int it = 0;; ++it, ++acc_it) {
+          bool have;
+          if (phase == 0) {
+            have = it1.valid();
+            if (have) {
+              t.m_blk = 2 * it1.mp + rm;
+              t.n = it1.n;
+              t.kb_begin = 0;
+              t.kb_end = g.nkb1;
+              t.slice = 0;
+              it1.next();          // (it1 now describes the pair's NEXT tile)
+            }
+          } else {
+            have = item3(g, it, p, P, rm, t);
+          }
+          if (!have) break;
           const int as = acc_it & 1;
           bool last_of_run = false;
           if (res1) {
@@ -730,8 +772,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
               tc::mbar_wait(&bars->a_full, a_runs & 1u);
               ++a_runs;
             }
-            Item nx;
-            last_of_run = !item1(g, it + 1, p, P, rm, nx) || (nx.m_blk >> 1) != cur_mp;
+            last_of_run = !it1.valid() || it1.mp != cur_mp;
           }
 #if MOE_TRACE
           if (lane == 0 && acc_it == 4 && g.items1 > 5 * P) TRACE(50);
@@ -1517,21 +1558,36 @@ int moe_ffn_fused(const void* x, const void* w1p, const float* b1p, const void* 
   // from 26 KB to 10 KB per k-block and CTA.  Measured slower (d = 320: 39.5 vs 37.2 us per layer call): the panels
   // take 80 KB away from the W1 ring, and with less than two tiles of W1 in flight the ring's round trip
   // (MMA complete -> slot free -> TMA -> landed) paces the tiles.  Off by default; kept for parity tests of the path.
-  g.tail_off = g.stages * g.slot_bytes + 2 * g.hs_bytes;
+  g.hs_off = g.stages * g.slot_bytes;
+  g.tail_off = g.hs_off + 2 * g.hs_bytes;
   g.sep_ring1 = 0;
   g.ring1_off = 0;
   g.direct_h = 0;
   g.a_resident = 0;
   g.a_res_bytes = g.nkb1 * kABytes;
   g.slot1_bytes = g.ks1 * nv * 128;
-  g.stages1 = (g.stages * g.slot_bytes - g.a_res_bytes) / g.slot1_bytes;
-  if (g.stages1 > kMaxStages) g.stages1 = kMaxStages;
-  if (const char* e = getenv("MOE_FUSED_ARES")) g.a_resident = (atoi(e) != 0 && g.stages1 >= 2 && g.items1 >= P && g.nkb1 <= 8) ? 1 : 0;
-  if (g.a_resident) {
-    g.step_m1 = 0;
-    g.step_n1 = 1;
-    g.sep_ring1 = 1;
-    g.ring1_off = g.a_res_bytes;
+  {
+    // resident panels + the W1 ring over the WHOLE area in front of the staging buffers
+    const int region = (kSmemLimit - fixed) / 1024 * 1024;
+    int ares_ks = g.ks1;
+    if (const char* e = getenv("MOE_FUSED_ARES_KS")) ares_ks = atoi(e) == 1 ? 1 : g.ks1;
+    const int slot1 = ares_ks * nv * 128;
+    int stages1 = (region - g.a_res_bytes) / slot1;
+    if (stages1 > kMaxStages) stages1 = kMaxStages;
+    bool on = false;
+    if (const char* e = getenv("MOE_FUSED_ARES")) on = atoi(e) != 0;
+    if (on && stages1 >= 2 && g.items1 >= P && g.nkb1 <= 8) {
+      g.a_resident = 1;
+      g.ks1 = ares_ks;
+      g.slot1_bytes = slot1;
+      g.stages1 = stages1;
+      g.hs_off = region > g.stages * g.slot_bytes ? region : g.stages * g.slot_bytes;
+      g.tail_off = g.hs_off + 2 * g.hs_bytes;
+      g.step_m1 = 0;
+      g.step_n1 = 1;
+      g.sep_ring1 = 1;
+      g.ring1_off = g.a_res_bytes;
+    }
   }
   // ---- direct-H mode of phase 1 (experimental, MOE_FUSED_DIRECT=1): the epilogue threads store their H rows straight
   // to global memory and the 2 x 20 KB of staging become a fourth ring slot for phase 1 (phase 3 keeps the staging for
