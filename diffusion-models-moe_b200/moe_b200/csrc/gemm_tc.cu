@@ -364,7 +364,7 @@ __device__ __forceinline__ PipeBarriers* setup_pipeline(uint8_t*& smem, uint8_t*
     for (int i = 0; i < g.stages; ++i) {
       tc::mbar_init(&bars->full[i], 1);
       tc::mbar_init(&bars->empty[i], PAIR ? 1u : static_cast<uint32_t>(g.cn + g.cm - 1));
-      tc::mbar_init(&bars->masked[i], 1);
+      tc::mbar_init(&bars->masked[i], kEpiWarps);   // one arrive per epilogue warp (the maskers)
     }
     for (int i = 0; i < 2; ++i) {
       tc::mbar_init(&bars->tmem_full[i], 1);
@@ -612,83 +612,65 @@ struct DownArgs {
   int h;
 };
 
-// Weight-masked down-projection (WandaRemoveNeuronsFast): warp 2 edits every landed W2 tile in shared memory --
-// a 16-bit zero store per set mask bit (Wanda masks are 2-12 % dense) -- between the TMA's `full` and the MMA
-// thread's `masked` barrier, so the masked weights never exist in global memory: DRAM traffic per call = W2 + the
-// mask bits (d h / 8 bytes), against W2 read + masked copy written + masked copy read for moe_mask_weights + K3.
-// The bit words of the NEXT stage are fetched into registers before the current stage is waited for (one L2 / HBM
-// round trip per stage would otherwise pace the ring).  A lane owns rows lane, lane + 32, ... of the B tile
-// (<= 8 rows: tile_n <= 256); a stage holds <= 2 k-blocks (the host caps ks at 2 for this form).
-constexpr int kMaskRows = 8, kMaskSubs = 2;
+// Weight-masked down-projection (WandaRemoveNeuronsFast): the 16 epilogue warps -- idle while a tile's main loop runs --
+// edit every landed W2 tile in shared memory, a 16-bit zero store per set mask bit (Wanda masks are 2-12 % dense), between
+// the TMA's `full` and the MMA thread's `masked` barrier, so the masked weights never exist in global memory: DRAM traffic
+// per call = W2 + the mask bits (d h / 8 bytes).  Warp w owns rows [w * tile_n / 16, ...) of the B tile, two lanes per row
+// (32 of a k-block's 64 mask bits each); the bit words of the NEXT stage are fetched before the current one is waited
+// for.  Cost against the unmasked kernel: the epilogue of tile i no longer overlaps the main loop of tile i + 1 (the same
+// warps mask first, then drain the accumulator).  (Round 2's first version used ONE masker warp: 2-8x slower than
+// mask_weights + down_proj, profiles/r02_wanda_masked_k3.log.)
+constexpr int kMaskSubs = 2;     // k-blocks per stage the masked form supports (the host caps ks)
 
-__device__ __forceinline__ void mask_fetch(const GemmShape& g, const DownArgs& a, const TileCoord& t, int kb, int lane,
-                                           uint2 (&bits)[kMaskRows * kMaskSubs]) {
+struct MaskState {
+  int s;
+  uint32_t ph;
+};
+
+__device__ __forceinline__ void mask_fetch(const GemmShape& g, const DownArgs& a, const TileCoord& t, int kb, int row, int half,
+                                           bool row_ok, uint32_t (&bits)[kMaskSubs]) {
   const int n_sub = min(g.ks, t.kb_end - kb);
+  const int grow = t.n_blk * g.tile_n + row;
 #pragma unroll
   for (int sub = 0; sub < kMaskSubs; ++sub)
-#pragma unroll
-    for (int r = 0; r < kMaskRows; ++r) {
-      const int j = lane + 32 * r;
-      const int grow = t.n_blk * g.tile_n + j;
-      uint2 v = make_uint2(0u, 0u);
-      if (sub < n_sub && j < g.tile_n && grow < a.d)     // (rows beyond d are zero-filled by the TMA anyway)
-        v = __ldg(reinterpret_cast<const uint2*>(a.mask_bits + ((static_cast<size_t>(grow) * a.h) >> 5)) + (kb + sub));
-      bits[sub * kMaskRows + r] = v;
-    }
+    bits[sub] = (row_ok && sub < n_sub && grow < a.d)      // (rows beyond d are zero-filled by the TMA anyway)
+                    ? __ldg(a.mask_bits + ((static_cast<size_t>(grow) * a.h) >> 5) + 2 * (kb + sub) + half)
+                    : 0u;
 }
 
-__device__ __forceinline__ void mask_loop(uint8_t* smem, PipeBarriers* bars, const GemmShape& g, const DownArgs& a,
-                                          int rn, int rm, int lane) {
-  int s = 0;
-  uint32_t ph = 0;
-  TileCoord t, tn;
-  uint2 cur[kMaskRows * kMaskSubs], nxt[kMaskRows * kMaskSubs];
-  bool have = tile_at(g, 0, rn, rm, t);
-  if (have) mask_fetch(g, a, t, t.kb_begin, lane, cur);
-  for (int it = 0; have; ++it) {
-    const bool have_next_tile = tile_at(g, it + 1, rn, rm, tn);
-    for (int kb = t.kb_begin; kb < t.kb_end; kb += g.ks) {
-      // next stage's bit words: in flight while this stage is waited for and edited
-      const bool more = kb + g.ks < t.kb_end;
-      if (more)
-        mask_fetch(g, a, t, kb + g.ks, lane, nxt);
-      else if (have_next_tile)
-        mask_fetch(g, a, tn, tn.kb_begin, lane, nxt);
-      tc::mbar_wait(&bars->full[s], ph);
-      const uint32_t b_base = tc::smem_u32(smem + s * g.stage_bytes) + g.ks * kABytes;
+// mask every stage of tile t's main loop as it lands (called by all lanes of every epilogue warp)
+__device__ __forceinline__ void mask_tile(uint8_t* smem, PipeBarriers* bars, const GemmShape& g, const DownArgs& a,
+                                          const TileCoord& t, int ew, int lane, MaskState& ms) {
+  const int rpw = g.tile_n / kEpiWarps;                 // rows of the B tile per warp (tile_n is a multiple of 16)
+  const int row = ew * rpw + (lane >> 1), half = lane & 1;
+  const bool row_ok = (lane >> 1) < rpw;
+  uint32_t cur[kMaskSubs], nxt[kMaskSubs];
+  mask_fetch(g, a, t, t.kb_begin, row, half, row_ok, cur);
+  for (int kb = t.kb_begin; kb < t.kb_end; kb += g.ks) {
+    if (kb + g.ks < t.kb_end) mask_fetch(g, a, t, kb + g.ks, row, half, row_ok, nxt);
+    tc::mbar_wait(&bars->full[ms.s], ms.ph);
+    const uint32_t b_base = tc::smem_u32(smem + ms.s * g.stage_bytes) + g.ks * kABytes;
 #pragma unroll
-      for (int sub = 0; sub < kMaskSubs; ++sub)
-#pragma unroll
-        for (int r = 0; r < kMaskRows; ++r) {
-          const int j = lane + 32 * r;
-          // 128-byte-swizzled K-major tile: 16-byte chunk c of row j sits at chunk (c ^ (j & 7))
-          const uint32_t row = b_base + static_cast<uint32_t>(sub * g.tile_n + j) * 128u;
-          const uint32_t sw = static_cast<uint32_t>(j & 7);
-          uint32_t w = cur[sub * kMaskRows + r].x;
-          while (w) {
-            const uint32_t b = static_cast<uint32_t>(__ffs(w) - 1);
-            w &= w - 1;
-            asm volatile("st.shared.u16 [%0], %1;" ::"r"(row + (((b >> 3) ^ sw) << 4) + ((b & 7u) << 1)), "h"(static_cast<unsigned short>(0)) : "memory");
-          }
-          w = cur[sub * kMaskRows + r].y;
-          while (w) {
-            const uint32_t b = 32u + static_cast<uint32_t>(__ffs(w) - 1);
-            w &= w - 1;
-            asm volatile("st.shared.u16 [%0], %1;" ::"r"(row + (((b >> 3) ^ sw) << 4) + ((b & 7u) << 1)), "h"(static_cast<unsigned short>(0)) : "memory");
-          }
-        }
-      tc::fence_proxy_async_smem();      // generic-proxy edits -> the tensor core's async-proxy reads
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&bars->masked[s]);
-#pragma unroll
-      for (int i = 0; i < kMaskRows * kMaskSubs; ++i) cur[i] = nxt[i];
-      if (++s == g.stages) {
-        s = 0;
-        ph ^= 1u;
+    for (int sub = 0; sub < kMaskSubs; ++sub) {
+      // 128-byte-swizzled K-major tile: 16-byte chunk c of row j sits at chunk (c ^ (j & 7))
+      const uint32_t rowaddr = b_base + static_cast<uint32_t>(sub * g.tile_n + row) * 128u;
+      const uint32_t sw = static_cast<uint32_t>(row & 7);
+      uint32_t w = cur[sub];
+      while (w) {
+        const uint32_t b = static_cast<uint32_t>(32 * half) + static_cast<uint32_t>(__ffs(w) - 1);
+        w &= w - 1;
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(rowaddr + (((b >> 3) ^ sw) << 4) + ((b & 7u) << 1)), "h"(static_cast<unsigned short>(0)) : "memory");
       }
     }
-    have = have_next_tile;
-    t = tn;
+    tc::fence_proxy_async_smem();      // generic-proxy edits -> the tensor core's async-proxy reads
+    __syncwarp();
+    if (lane == 0) tc::mbar_arrive(&bars->masked[ms.s]);
+#pragma unroll
+    for (int i = 0; i < kMaskSubs; ++i) cur[i] = nxt[i];
+    if (++ms.s == g.stages) {
+      ms.s = 0;
+      ms.ph ^= 1u;
+    }
   }
 }
 
@@ -707,8 +689,6 @@ down_proj_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_consta
     producer_loop<PAIR>(&tmap_h, &tmap_w2, smem, bars, g, rn, rm, warp == 0);   // warp-converged; one elected lane issues
   } else if (warp == 1) {
     if (!PAIR || rm == 0) mma_loop<PAIR, MASK>(smem, bars, g, tmem_base, rn, rm);   // pair: the leader CTA issues for both
-  } else if (warp == 2) {
-    if constexpr (MASK) mask_loop(smem, bars, g, a, rn, rm, lane);
   } else if (warp >= kEpiWarp0) {
     const int ew = warp - kEpiWarp0;
     const int q = warp & 3;
@@ -716,11 +696,13 @@ down_proj_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_consta
     const int cpg = g.tile_n / kColGroups;
     float* sbias = reinterpret_cast<float*>(extra) + ew * (kBiasSmemPerWarp / 4);
     TileCoord t;
+    MaskState ms = {0, 0u};
     for (int it = 0; tile_at(g, it, rn, rm, t); ++it) {
       const int as = it & 1;
       const uint32_t aph = (it >> 1) & 1u;
       const int n0 = t.n_blk * g.tile_n + cg * cpg;    // first output column of this warp's group
       const int nvalid = max(0, min(cpg, a.d - n0));   // the last tile may overhang d
+      if constexpr (MASK) mask_tile(smem, bars, g, a, t, ew, lane, ms);   // this tile's W2 stages, as they land
       stage_bias(sbias, a.b2 != nullptr ? a.b2 + n0 : nullptr, nullptr, nvalid, lane);
       tc::mbar_wait(&bars->tmem_full[as], aph);
       tc::fence_after_thread_sync();
@@ -1280,7 +1262,7 @@ static int down_proj_impl(const void* H, const void* w2p, const uint32_t* mask_b
   a.mask_bits = mask_bits;
   a.h = h;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (masked) MOE_REQUIRE(g.cn == 1 && g.cm == 1 && !g.pair && g.tile_n <= 32 * kMaskRows && g.ks <= kMaskSubs,
+  if (masked) MOE_REQUIRE(g.cn == 1 && g.cm == 1 && !g.pair && g.tile_n % kEpiWarps == 0 && g.ks <= kMaskSubs,
                           MOE_ERR_UNSUPPORTED_SHAPE, "moe_down_proj_masked: tile shape not supported");
 #define MOE_LAUNCH_DOWN(CHV)                                                                   \
   rc = masked ? launch_clustered(down_proj_kernel<CHV, false, true>, g, st, th, tw, g, a)       \

@@ -11,8 +11,8 @@ down-projection.  `mask_mode`:
     'cache'  (default) resident masked weights, up to `cache_bytes`; cells beyond the budget fall back to 'copy'
     'copy'   two launches per call: moe_mask_weights into a scratch copy, then moe_down_proj (+2.4 .. 6 us per call)
     'fused'  one launch, no copy at all: moe_down_proj_masked applies the bits to the W2 tiles in shared memory
-             between the TMA and the tensor core (measured 2-8x slower than 'copy': one masker warp per CTA cannot
-             keep up with the tensor pipe, profiles/r02_wanda_masked_k3.log; kept for memory-constrained use)"""
+             between the TMA and the tensor core (the 16 epilogue warps mask; within 8 % of 'copy' at the batch-2
+             shapes with sparse masks, slower at large T / dense masks: profiles/r02_wanda_masked_k3_v2.log)"""
 import os
 import pickle
 

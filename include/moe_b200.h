@@ -157,9 +157,9 @@ MOE_API size_t moe_down_grouped_workspace_bytes(int T, int k, int E, int d);
 MOE_API int moe_down_proj(const void* H, const void* w2p, const float* b2, void* Y, int T, int h, int d,
                   void* workspace, size_t workspace_bytes, void* stream);
 /* K3 with an elementwise weight mask applied on the fly: Y = H (W2 * (1 - M))^T + b2, M given as bit words over the
- * row-major [d, h] weight (bit r*h + c; the layout of moe_mask_pack / moe_mask_union / moe_wanda_score_mask).  A masker
- * warp zeroes the masked weights of every landed W2 tile in shared memory, between the TMA and the tensor core, so no
- * masked copy of W2 is ever written: one launch, DRAM traffic = W2 + d*h/8 bytes of mask.
+ * row-major [d, h] weight (bit r*h + c; the layout of moe_mask_pack / moe_mask_union / moe_wanda_score_mask).  The
+ * epilogue warps zero the masked weights of every landed W2 tile in shared memory, between the TMA and the tensor core,
+ * so no masked copy of W2 is ever written: one launch, DRAM traffic = W2 + d*h/8 bytes of mask.
  * Replaces: remove_wanda_neurons_fast.py:72-77 (H2D of a dense int64 mask, W.clone(), W*(1-mask), F.linear) per call.
  * Requirements: h % 64 == 0, mask_bits 8-byte aligned; otherwise MOE_ERR_UNSUPPORTED_SHAPE and the caller uses
  * moe_mask_weights + moe_down_proj.  Workspace: as moe_down_proj. */
