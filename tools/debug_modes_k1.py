@@ -1,5 +1,7 @@
+"""K1 (geglu_up, cta_group::2 pairs) with pipeline stages switched off: MOE_DEBUG_MODE bit 1 = TMA loads, 2 = MMAs,
+4 = epilogue TMEM read + math (results are garbage in those modes, timing only) -- profiles/r02_phase1_cadence.log."""
 import os, sys, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "diffusion-models-moe_b200"))
 import moe_b200 as M
 dev = "cuda:0"; REPS = 6

@@ -1,6 +1,9 @@
+"""Raw %globaltimer stamps of the fused kernel for a few CTAs (trace build: MOE_LIB_VARIANT=trace build.py first):
+commit / epilogue begin / done of the first tiles and the MMA / producer warps' stamps of tile 4 (valid for <= 10 items per
+pair, i.e. T <= 8192 at d = 320) -- profiles/r02_phase1_cadence.log.    python tools/trace_fused_raw.py [T]"""
 import ctypes, os, sys
 import torch
-ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "diffusion-models-moe_b200"))
 os.environ.setdefault("MOE_LIB_VARIANT", "trace")
 import moe_b200 as M
