@@ -820,7 +820,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             tc::umma_commit_2sm_mc(&bars->tmem_full[as], 0x3);   // accumulator complete -> both epilogues
             if (last_of_run) tc::umma_commit_2sm_mc(&bars->a_empty, 0x3);   // the resident panels may be replaced
 #if MOE_TRACE
-            if (acc_it < 13) TRACE(8 + 4 * acc_it);
+            if (acc_it < 8) TRACE(8 + 4 * acc_it);
 #endif
           }
           __syncwarp();
@@ -897,7 +897,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             n_pend = 0;
 #if MOE_TRACE
             if (it >= 2 && it < 4) TRACE(42 + 4 * (it - 2));
-            if (st_it - 1 < 13) TRACE(8 + 4 * (st_it - 1) + 3);
+            if (st_it - 1 < 8) TRACE(8 + 4 * (st_it - 1) + 3);
             if (it >= 2 && it < 4) TRACE(43 + 4 * (it - 2));
 #endif
           }
@@ -919,7 +919,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         for (int i = 0; i < kPubBatch; ++i)
           if (i < n_pend) atomicAdd(ws_rec + pend[i] * kBlockRecInts, 1);
 #if MOE_TRACE
-        if (st_it - 1 < 13) TRACE(8 + 4 * (st_it - 1) + 3);
+        if (st_it - 1 < 8) TRACE(8 + 4 * (st_it - 1) + 3);
 #endif
       }
       __syncwarp();
@@ -1054,7 +1054,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         tc::mbar_wait(&bars->tmem_full[as], (acc_it >> 1) & 1u);
         tc::fence_after_thread_sync();
 #if MOE_TRACE
-        if (ew == 0 && lane == 0 && acc_it < 13) TRACE(8 + 4 * acc_it + 1);
+        if (ew == 0 && lane == 0 && acc_it < 8) TRACE(8 + 4 * acc_it + 1);
 #endif
         // (the alignment of the group's staging stores is warp-uniform: two instantiations, one uniform branch)
 #define MOE_GEGLU_CALL(ACT_, AL_, DIR_) \
@@ -1092,7 +1092,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&bars->hs_full[buf]);
 #if MOE_TRACE
-        if (ew == 0 && lane == 0 && acc_it < 13) TRACE(8 + 4 * acc_it + 2);
+        if (ew == 0 && lane == 0 && acc_it < 8) TRACE(8 + 4 * acc_it + 2);
 #endif
       }
       use0 = (it + 1) >> 1;
@@ -1136,7 +1136,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         tc::mbar_wait(&bars->tmem_full[as], (acc_it >> 1) & 1u);
         tc::fence_after_thread_sync();
 #if MOE_TRACE
-        if (ew == 0 && lane == 0 && acc_it < 13) TRACE(8 + 4 * acc_it + 1);
+        if (ew == 0 && lane == 0 && acc_it < 8) TRACE(8 + 4 * acc_it + 1);
 #endif
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + as * kAccStride + col0;
         const int row = t.m_blk * kBlockM + q_row;
@@ -1258,7 +1258,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           tc::named_bar_sync(1, kEpiThreads);
         }
 #if MOE_TRACE
-        if (ew == 0 && lane == 0 && acc_it < 13) TRACE(8 + 4 * acc_it + 2);
+        if (ew == 0 && lane == 0 && acc_it < 8) TRACE(8 + 4 * acc_it + 2);
 #endif
       }
     }
