@@ -169,8 +169,9 @@ class SyntheticFFNPipeline:
         steps = num_inference_steps or self.num_inference_steps
         batch = 2 * len(prompts)
         shapes = sd_ffn_shapes(self.unet.latent_hw)
-        gen = torch.Generator(device="cpu").manual_seed(int(torch.initial_seed()) % (2 ** 31))
-        states = [torch.randn(batch, s, d, generator=gen).to(self.device, self.dtype) for (_, d, _, s) in shapes]
+        # seeded synthetic hidden states, drawn on the pipeline's device (no host round trip per call)
+        gen = torch.Generator(device=self.device).manual_seed(int(torch.initial_seed()) % (2 ** 31))
+        states = [torch.randn(batch, s, d, generator=gen, device=self.device).to(self.dtype) for (_, d, _, s) in shapes]
         for _ in range(steps):
             # the residual stream of every block carries over to the next step (each block normalises its own
             # FFN input with norm3, so the FFN sees O(1) activations at every step)
