@@ -336,7 +336,6 @@ __device__ __forceinline__ bool item3(const Shape& g, int it, int p, int P, int 
 }
 
 using route::route_chunk;
-using route::route_dispatch;
 
 // phase-1 tiles of a pair without divisions in the loop (the MMA warp walks its list on the critical path of every
 // tile: item1() costs ~0.4 us of integer divisions per call)
@@ -659,7 +658,6 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 #if MOE_TRACE
             if (it == 0) TRACE(63);
 #endif
-            block_consumed(ws_rec + t.m_blk * kBlockRecInts, 2 * g.n_tiles3 * g.split3);
           }
           __syncwarp();
           fence_proxy_async_global();   // generic-proxy writes of other SMs (acquired above) -> this thread's TMA reads
@@ -684,10 +682,12 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         for (int kb = t.kb_begin; kb < t.kb_end; kb += ks) {
 #if MOE_TRACE
           if (do_a && lane == 0 && phase == 0 && it == 4 && kb == t.kb_begin && g.items1 > 5 * P) TRACE(54);
+          if (do_a && lane == 0 && phase == 1 && it == 0 && kb == t.kb_begin && g.items1 <= 5 * P) TRACE(54);
 #endif
           tc::mbar_wait(&empty_bar[s], ph ^ 1u);
 #if MOE_TRACE
           if (do_a && lane == 0 && phase == 0 && it == 4 && kb + ks >= t.kb_end && g.items1 > 5 * P) TRACE(55);
+          if (do_a && lane == 0 && phase == 1 && it == 0 && kb + ks >= t.kb_end && g.items1 <= 5 * P) TRACE(55);
 #endif
           uint8_t* sa = ring + s * slot_bytes;
           uint8_t* sb = res1 ? sa : sa + ks * kABytes;
@@ -718,6 +718,9 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             ph ^= 1u;
           }
         }
+        // (the visit count of the block's record -- an atomic with a returned value, one L2 round trip -- after the
+        // item's loads have been issued, not between the ready-wait and the first load)
+        if (phase == 1 && do_a && lane == 0) block_consumed(ws_rec + t.m_blk * kBlockRecInts, 2 * g.n_tiles3 * g.split3);
       }
     }
   } else if (warp == 1) {
@@ -776,11 +779,13 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           }
 #if MOE_TRACE
           if (lane == 0 && acc_it == 4 && g.items1 > 5 * P) TRACE(50);
+          if (lane == 0 && phase == 1 && it == 0 && g.items1 <= 5 * P) TRACE(50);
 #endif
           tc::mbar_wait(&bars->tmem_empty[as], ((acc_it >> 1) & 1u) ^ 1u);
           tc::fence_after_thread_sync();
 #if MOE_TRACE
           if (lane == 0 && acc_it == 4 && g.items1 > 5 * P) TRACE(51);
+          if (lane == 0 && phase == 1 && it == 0 && g.items1 <= 5 * P) TRACE(51);
 #endif
           const uint32_t d_tmem = tb + as * kAccStride;
           for (int kb = t.kb_begin; kb < t.kb_end; kb += ks) {
@@ -788,6 +793,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             tc::fence_after_thread_sync();
 #if MOE_TRACE
             if (lane == 0 && acc_it == 4 && g.items1 > 5 * P) TRACE(kb == t.kb_begin ? 52 : 53);
+            if (lane == 0 && phase == 1 && it == 0 && g.items1 <= 5 * P) TRACE(kb == t.kb_begin ? 52 : 53);
 #endif
             const uint32_t slot = ring + s * slot_bytes;
             const uint32_t a_base = res1 ? a_res + static_cast<uint32_t>(kb) * kABytes : slot;
@@ -1109,14 +1115,24 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 #if MOE_TRACE
         if (ew == 0 && lane == 0 && idx == 0) TRACE(60);
 #endif
-        for (int c = ti.n * g.split3 + ti.slice; c < g.chunks_per_block; c += g.n_tiles3 * g.split3)
-          route_dispatch(g, a, ti.m_blk * kBlockM + c * g.chunk_tokens, min(g.T, (ti.m_blk + 1) * kBlockM), ew, lane, s_words,
-                         s_hist);
-        __syncwarp();        // every lane's zero-writes / labels before lane 0's arrive (release at CTA scope; the sync
-        if (lane == 0) tc::mbar_arrive(&bars->route_done);   // warp's red.release then publishes them device-wide)
+        // per chunk: select -> zero-writes -> (after the item's last chunk) signal -> labels / histogram.  The signal
+        // follows a __syncwarp: every lane's zero-writes precede lane 0's arrive (release at CTA scope; the sync warp's
+        // red.release then publishes them device-wide).  Labels and counters are kernel outputs nobody waits for.
+        const int consumers = g.n_tiles3 * g.split3;
+        const int c0 = ti.n * g.split3 + ti.slice;
+        auto signal = [&] {
+          if (lane == 0) tc::mbar_arrive(&bars->route_done);
 #if MOE_TRACE
-        if (ew == 0 && lane == 0) TRACE(61);
+          if (ew == 0 && lane == 0) TRACE(61);
 #endif
+        };
+        if (c0 >= g.chunks_per_block) {       // more consumers than chunks: nothing to route for this item
+          __syncwarp();
+          signal();
+        }
+        for (int c = c0; c < g.chunks_per_block; c += consumers)
+          route::route_dispatch_ordered(g, a, ti.m_blk * kBlockM + c * g.chunk_tokens, min(g.T, (ti.m_blk + 1) * kBlockM), ew,
+                                        lane, s_words, s_hist, c + consumers >= g.chunks_per_block, signal);
       };
       if (item3(g, 0, p, P, rm, t)) route_item(t, 0);
       for (int it = 0; item3(g, it, p, P, rm, t); ++it, ++acc_it) {
@@ -1188,7 +1204,9 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           if (ew == 0 && lane == 0 && it == 0) TRACE(48);
 #endif
           // all partial stores of the CTA, then ONE releasing increment: it publishes this slice's partial tile; the
-          // last slice to arrive reads the other slices' tiles from L2 (ld.cg) after the barrier below
+          // last slice to arrive reads the other slices' tiles from L2 (ld.cg) after the barrier below.  (Letting every
+          // slice wait for the others and reduce its share of the rows was measured 2 us SLOWER at d = 1280 / 512
+          // tokens: all slices then end with the slowest one, plus a poll and an L2 round trip.)
           tc::named_bar_sync(1, kEpiThreads);
           if (ew == 0 && lane == 0) {
             int* counter = a.split_counters + t.m_blk * g.n_tiles3 + t.n;
@@ -1228,18 +1246,32 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 #pragma unroll
               for (int u = 0; u < kU; ++u) {
                 const int e = e0 + u * kEpiThreads;
-                if (e >= total) break;
-                const int r = e & (kBlockM - 1), c4i = e >> 7;
-                const int gcol = tile_col0 + 4 * c4i;
-                float4 sum = (a.b2 != nullptr && gcol < g.d) ? __ldg(reinterpret_cast<const float4*>(a.b2 + gcol))
-                                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+                const int gcol = tile_col0 + 4 * (e >> 7);
+                float4 sum = (e < total && a.b2 != nullptr && gcol < g.d) ? __ldg(reinterpret_cast<const float4*>(a.b2 + gcol))
+                                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
                 sum.x += p0[u].x; sum.y += p0[u].y; sum.z += p0[u].z; sum.w += p0[u].w;     // slice order: deterministic
                 sum.x += p1[u].x; sum.y += p1[u].y; sum.z += p1[u].z; sum.w += p1[u].w;
-                for (int sl = 2; sl < g.split3; ++sl) {
-                  const float4 v = __ldcg(src + sl * g.split_plane4 + c4i * kBlockM + r);
-                  sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+                p0[u] = sum;
+              }
+              // further slices one at a time, the trip's chunks of a slice in flight together (one L2 round trip per
+              // slice; a load-and-add per chunk and slice was 2 x kU dependent round trips at split 4)
+              for (int sl = 2; sl < g.split3; ++sl) {
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                  const int e = e0 + u * kEpiThreads;
+                  if (e < total) p1[u] = __ldcg(src + sl * g.split_plane4 + (e >> 7) * kBlockM + (e & (kBlockM - 1)));
                 }
-                tc::sts_b32x2(stage_addr(ybase, hl3, r, 4 * c4i), pack_bf16x2(sum.x, sum.y), pack_bf16x2(sum.z, sum.w));
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                  p0[u].x += p1[u].x; p0[u].y += p1[u].y; p0[u].z += p1[u].z; p0[u].w += p1[u].w;
+                }
+              }
+#pragma unroll
+              for (int u = 0; u < kU; ++u) {
+                const int e = e0 + u * kEpiThreads;
+                if (e >= total) break;
+                tc::sts_b32x2(stage_addr(ybase, hl3, e & (kBlockM - 1), 4 * (e >> 7)), pack_bf16x2(p0[u].x, p0[u].y),
+                              pack_bf16x2(p0[u].z, p0[u].w));
               }
             }
             tc::fence_proxy_async_smem();

@@ -30,9 +30,15 @@ __device__ __forceinline__ uint32_t float_key(float s) {
 // router's RouterGeom / RouterPtrs): fields used are g.{lanes, lanes_log2, E, k, words, mask_h, h, es_magic,
 // count_begin, count_end} and a.{scores, removed_bits, active_bits, idx, hist, H} (+ a.score_bias when kBias,
 // + the per-lane running score maxima `mx` when kColmax: the standalone router's extras).
+//
+// The work is split in three stages so that a caller can order them: route_select (scores -> the lane's selection mask
+// `sel`, expert-set words to shared and global memory), route_labels (ascending labels + histogram from `sel`) and
+// route_zero_row (write-only masking of one token row of H from its expert-set words).  route_chunk runs them in the
+// order select, labels, zero for the warp's own tokens (the standalone router); the fused layer kernel zeroes first,
+// signals the block's consumers and writes the labels afterwards, off the critical path of the down-projection.
 template <int KPT, bool kBias = false, bool kColmax = false, class G, class A>
-__device__ __forceinline__ void route_chunk(const G& g, const A& a, int tok0, int tok_end, int ew, int lane,
-                                            uint32_t* s_words, unsigned int* s_hist, float* mx = nullptr) {
+__device__ __forceinline__ uint32_t route_select(const G& g, const A& a, int tok0, int tok_end, int ew, int lane,
+                                                 uint32_t* s_words, float* mx = nullptr) {
   const unsigned full = 0xffffffffu;
   const int L = g.lanes;
   const int tpw = 32 >> g.lanes_log2;           // tokens per warp
@@ -264,7 +270,21 @@ __device__ __forceinline__ void route_chunk(const G& g, const A& a, int tok0, in
     s_words[tl * g.words + widx] = word;
     if (t_ok && a.active_bits != nullptr) a.active_bits[static_cast<size_t>(t) * g.words + widx] = word;
   }
+  return sel;
+}
 
+// ascending labels and histogram of the warp's tokens from the lanes' selection masks
+template <int KPT, class G, class A>
+__device__ __forceinline__ void route_labels(const G& g, const A& a, uint32_t sel, int tok0, int tok_end, int ew, int lane,
+                                             unsigned int* s_hist) {
+  const unsigned full = 0xffffffffu;
+  const int L = g.lanes;
+  const int tpw = 32 >> g.lanes_log2;
+  const int part = lane & (L - 1);
+  const int tl = lane >> g.lanes_log2;
+  const int t = tok0 + tpw * ew + tl;
+  const bool t_ok = t < tok_end;
+  const int e0 = part * KPT;
   if (a.idx != nullptr) {
     const int n_sel = __popc(sel);
     int incl = n_sel;
@@ -291,37 +311,51 @@ __device__ __forceinline__ void route_chunk(const G& g, const A& a, int tok0, in
       w &= w - 1;
     }
   }
+}
+
+// does the routing stage materialise the masked hidden state?  (k == E still masks the removed experts' neurons)
+template <class G, class A>
+__device__ __forceinline__ bool route_masks_h(const G& g, const A& a) {
+  return g.mask_h && (g.k < g.E || a.removed_bits != nullptr);
+}
+
+// Zero the neurons of every expert outside token `tok`'s active set (expert-set words at `wtok`), 16-byte units
+// [u_begin + lane, u_end) step 32 of its row of H: write-only, 4-neuron groups never straddle an expert because
+// es % 4 == 0.  Two predicated 8-byte stores per unit and no branches: a three-way if / else (16-byte store, or either
+// half) made the warp run each store flavour in turn.  (A variant that kept the expert words in registers and hoisted
+// the two divisions per unit out of the loop was measured 1.5 % SLOWER end to end: at UNet batch 16 this stage is
+// paced by the 7 TB/s of zero stores into L2, not by its instructions -- profiles/r02_route_ab.log.)
+template <class G, class A>
+__device__ __forceinline__ void route_zero_row(const G& g, const A& a, int tok, const uint32_t* wtok, int u_begin,
+                                               int u_end, int lane) {
+  uint4* hrow = reinterpret_cast<uint4*>(a.H + static_cast<size_t>(tok) * g.h);
+#pragma unroll 4
+  for (int u = u_begin + lane; u < u_end; u += 32) {
+    const uint32_t ea = __umulhi(static_cast<uint32_t>(u) << 3, g.es_magic);
+    const uint32_t eb = __umulhi((static_cast<uint32_t>(u) << 3) + 4u, g.es_magic);
+    const bool on_a = (wtok[ea >> 5] >> (ea & 31u)) & 1u;
+    const bool on_b = (wtok[eb >> 5] >> (eb & 31u)) & 1u;
+    uint2* half = reinterpret_cast<uint2*>(hrow + u);
+    if (!on_a) half[0] = make_uint2(0u, 0u);
+    if (!on_b) half[1] = make_uint2(0u, 0u);
+  }
+}
+
+template <int KPT, bool kBias = false, bool kColmax = false, class G, class A>
+__device__ __forceinline__ void route_chunk(const G& g, const A& a, int tok0, int tok_end, int ew, int lane,
+                                            uint32_t* s_words, unsigned int* s_hist, float* mx = nullptr) {
+  const uint32_t sel = route_select<KPT, kBias, kColmax>(g, a, tok0, tok_end, ew, lane, s_words, mx);
+  route_labels<KPT>(g, a, sel, tok0, tok_end, ew, lane, s_hist);
   __syncwarp();
 #if MOE_ROUTE_TRACE
   if (ew == 0 && lane == 0) TRACE(58);
 #endif
-
-  if (g.mask_h && (g.k < E || a.removed_bits != nullptr)) {   // k == E still masks the removed experts' neurons
-    // materialise the masked hidden state: zero the neurons of every expert outside the token's active set
-    // (write-only; 16-byte units, 4-neuron groups never straddle an expert because es % 4 == 0)
-    const int units = g.h >> 3;
-    // (A variant that kept the tokens' expert words in registers and hoisted the two divisions per unit out of the
-    // token loop was measured 1.5 % SLOWER end to end: this stage is paced by the 7 TB/s of zero stores into L2, not
-    // by its instructions -- profiles/r02_route_ab.log.)
-    {
+  if (route_masks_h(g, a)) {
+    const int tpw = 32 >> g.lanes_log2;
     for (int tt = 0; tt < tpw; ++tt) {
       const int tok = tok0 + tpw * ew + tt;
       if (tok >= tok_end) break;
-      const uint32_t* wtok = s_words + tt * g.words;
-      uint4* hrow = reinterpret_cast<uint4*>(a.H + static_cast<size_t>(tok) * g.h);
-      // two predicated 8-byte stores per 16-byte unit and no branches: a three-way if / else (16-byte store, or
-      // either half) made the warp run each store flavour in turn
-#pragma unroll 4
-      for (int u = lane; u < units; u += 32) {
-        const uint32_t ea = __umulhi(static_cast<uint32_t>(u) << 3, g.es_magic);
-        const uint32_t eb = __umulhi((static_cast<uint32_t>(u) << 3) + 4u, g.es_magic);
-        const bool on_a = (wtok[ea >> 5] >> (ea & 31u)) & 1u;
-        const bool on_b = (wtok[eb >> 5] >> (eb & 31u)) & 1u;
-        uint2* half = reinterpret_cast<uint2*>(hrow + u);
-        if (!on_a) half[0] = make_uint2(0u, 0u);
-        if (!on_b) half[1] = make_uint2(0u, 0u);
-      }
-    }
+      route_zero_row(g, a, tok, s_words + tt * g.words, 0, g.h >> 3, lane);
     }
   }
   __syncwarp();
@@ -330,17 +364,56 @@ __device__ __forceinline__ void route_chunk(const G& g, const A& a, int tok0, in
 #endif
 }
 
-template <class G, class A>
-__device__ __forceinline__ void route_dispatch(const G& g, const A& a, int tok0, int tok_end, int ew, int lane,
-                                               uint32_t* s_words, unsigned int* s_hist) {
-  if (ew >= g.route_warps) return;   // small chunks (many consumers per block) use only the first warps
-  switch (g.kpt) {
-    case 16: route_chunk<16>(g, a, tok0, tok_end, ew, lane, s_words, s_hist); break;
-    case 8: route_chunk<8>(g, a, tok0, tok_end, ew, lane, s_words, s_hist); break;
-    case 4: route_chunk<4>(g, a, tok0, tok_end, ew, lane, s_words, s_hist); break;
-    case 2: route_chunk<2>(g, a, tok0, tok_end, ew, lane, s_words, s_hist); break;
-    case 1: route_chunk<1>(g, a, tok0, tok_end, ew, lane, s_words, s_hist); break;
-    default: break;
+// The fused layer kernel's order: select -> zero-writes -> signal -> labels.  `signal` tells the block's consumers that
+// the chunk's rows of H are masked (called by every warp, only after the item's last chunk); labels and histogram
+// follow it: nobody waits for them before the kernel ends.  (Spreading a token row's zero-writes over the warps that
+// do not route -- chunks of 4 tokens at d = 1280 -- was measured 0.4 us SLOWER per layer call: the stage is a store
+// round trip, not an instruction count, and the variant needs two more 512-thread barriers.  Publishing a block's
+// scores under their own counter, ahead of its H tile stores, so that the selection overlaps the stores' completion
+// was neutral to 0.8 us slower: the pair's last tile then pays two GPU-scope fences in a row.)
+template <class G, class A, class Signal>
+__device__ __forceinline__ void route_dispatch_ordered(const G& g, const A& a, int tok0, int tok_end, int ew, int lane,
+                                                       uint32_t* s_words, unsigned int* s_hist, bool last_chunk,
+                                                       Signal signal) {
+  const bool routing_warp = ew < g.route_warps;   // small chunks (many consumers per block) use only the first warps
+  uint32_t sel = 0u;
+  if (routing_warp) {
+    switch (g.kpt) {
+      case 16: sel = route_select<16>(g, a, tok0, tok_end, ew, lane, s_words); break;
+      case 8: sel = route_select<8>(g, a, tok0, tok_end, ew, lane, s_words); break;
+      case 4: sel = route_select<4>(g, a, tok0, tok_end, ew, lane, s_words); break;
+      case 2: sel = route_select<2>(g, a, tok0, tok_end, ew, lane, s_words); break;
+      case 1: sel = route_select<1>(g, a, tok0, tok_end, ew, lane, s_words); break;
+      default: break;
+    }
+  }
+  __syncwarp();
+#if MOE_ROUTE_TRACE
+  if (ew == 0 && lane == 0) TRACE(58);
+#endif
+  if (routing_warp && route_masks_h(g, a)) {
+    const int tpw = 32 >> g.lanes_log2;
+    for (int tt = 0; tt < tpw; ++tt) {
+      const int tok = tok0 + tpw * ew + tt;
+      if (tok >= tok_end) break;
+      route_zero_row(g, a, tok, s_words + tt * g.words, 0, g.h >> 3, lane);
+    }
+  }
+  __syncwarp();
+#if MOE_ROUTE_TRACE
+  if (ew == 0 && lane == 0) TRACE(59);
+#endif
+  if (last_chunk) signal();
+  if (routing_warp) {
+    switch (g.kpt) {
+      case 16: route_labels<16>(g, a, sel, tok0, tok_end, ew, lane, s_hist); break;
+      case 8: route_labels<8>(g, a, sel, tok0, tok_end, ew, lane, s_hist); break;
+      case 4: route_labels<4>(g, a, sel, tok0, tok_end, ew, lane, s_hist); break;
+      case 2: route_labels<2>(g, a, sel, tok0, tok_end, ew, lane, s_hist); break;
+      case 1: route_labels<1>(g, a, sel, tok0, tok_end, ew, lane, s_hist); break;
+      default: break;
+    }
+    __syncwarp();   // the next chunk's selection overwrites s_words / reuses the lanes' registers in lock step
   }
 }
 

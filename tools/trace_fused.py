@@ -48,6 +48,8 @@ def show(name, tr, ms):
     print(f"   MMA issuer, tile 4 (needs > 5 tiles per pair; us since tile 2 epi-done = its TMEM stage free): reaches tmem_empty wait {d(18,50)} | "
           f"stage free seen {d(18,51)} | first k-block landed {d(18,52)} | last k-block landed {d(18,53)} | commit issued {d(18,24)} | epi-begin {d(18,25)}")
     print(f"   A producer, tile 4 (same origin): reaches first slot wait {d(18,54)} | last slot free seen {d(18,55)} ; tile 3 commit issued {d(18,20)}")
+    print(f"   phase 3, first item (pairs with <= 5 phase-1 tiles; absolute us): A producer past the ready-wait {col(54)} | its last slot free {col(55)} | "
+          f"MMA thread at tmem wait {col(50)} | past it {col(51)} | first slot landed {col(52)} | last slot landed {col(53)}")
     print(f"   epi all done {col(4)} | teardown sync {col(5)} | exit {col(6)}")
 
 
