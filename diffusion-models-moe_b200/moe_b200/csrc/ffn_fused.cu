@@ -613,7 +613,12 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       if (bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
     }
   }
-  pdl_wait();   // everything above overlapped the previous kernel's tail
+  // Programmatic dependent launch: everything above overlapped the previous kernel's tail.  Only the warps whose FIRST
+  // access to memory the predecessor may touch is not already ordered behind another warp's wait execute
+  // griddepcontrol.wait: the A-tile producer (x, later the sync area) and the sync warp (sync area; a pair without
+  // phase-1 tiles polls it straight away).  The B-tile producer only ever reads the weights and starts filling the
+  // ring at once; the MMA thread, the epilogue warps and their stores follow the first x tile through mbarriers.
+  if (warp == 0 || warp == 2) pdl_wait();
   if (threadIdx.x == 0) pdl_launch_dependents();
   if (threadIdx.x == 0) TRACE(2);
   const uint32_t tmem_base = bars->tmem_base;
