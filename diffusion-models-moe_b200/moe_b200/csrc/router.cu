@@ -440,64 +440,102 @@ __global__ void __launch_bounds__(kPermWarps * 32) perm_scatter_kernel(const Per
 }
 
 // ------------------------------------------------------------------ K4 standalone histogram
-// 16-byte loads (8 labels per thread and load, four loads in flight), THREAD-PRIVATE 16-bit counters in shared memory
-// laid out [expert][thread]: a thread only ever touches its own column, so counting is a plain load / add / store --
-// no atomics, no match / ballot aggregation, at most a 2-way bank conflict (two 16-bit columns per bank) -- folded
-// once per CTA into one int64 global atomic per expert.  The grid is sized so that a thread counts at most
-// kHistMaxPerThread labels: a 16-bit counter cannot wrap.  (Round 1 aggregated equal labels with __match_any_sync first, 16 match
-// instructions per 16 bytes: 159 GB/s; per-warp bins with shared atomics: 921 GB/s.)
+// 16-byte loads (8 labels per thread and load, four loads in flight), THREAD-PRIVATE counters in shared memory: a thread
+// only ever touches its own counters, so counting is a plain load / add / store -- no atomics, no match / ballot
+// aggregation -- folded once per CTA into one int64 global atomic per expert.  Thread t's counters sit in the 32-bit
+// words row * kHistThreads + t, so the 32 lanes of a warp always hit 32 different banks, whatever their labels:
+//   kWide   (E <= kHistWideMaxE)  one 32-bit counter per expert (row = expert): 6 instructions per label
+//   packed                        two 16-bit counters per word (row = expert / 2, experts 2i / 2i + 1 in the low / high
+//                                 half): 9 instructions per label, half the shared memory; the grid is sized so that a
+//                                 thread counts at most kHistMaxPerThread labels and a half cannot carry into the other
+// Labels outside [0, E) (padding, -1) are clamped to one extra dump row instead of being branched around: the loop is
+// straight-line code with 32-bit shared addresses.  (The earlier versions were instruction-bound, not memory-bound: a
+// compare + branch + reconvergence pair + generic-address arithmetic per label, ~16 instructions, 2.5-2.7 TB/s whether
+// the 16-bit cells conflicted 2-way or not; round 1's __match_any_sync aggregation: 159 GB/s; per-warp bins with shared
+// atomics: 921 GB/s.)
 constexpr int kHistThreads = 128;
 constexpr int kHistMaxPerThread = 60000;
+constexpr int kHistWideMaxE = 64;
 
+template <bool kWide>
 __global__ void __launch_bounds__(kHistThreads) hist_accumulate_kernel(const int16_t* __restrict__ idx, long long n, int E,
                                                                        unsigned long long* __restrict__ hist) {
-  extern __shared__ unsigned short cnt[];      // [E][kHistThreads]
-  for (int i = threadIdx.x; i < E * kHistThreads / 2; i += blockDim.x) reinterpret_cast<unsigned int*>(cnt)[i] = 0u;
+  extern __shared__ unsigned int cnt[];        // [rows + 1][kHistThreads], rows = E (wide) or (E + 1) / 2 (packed)
+  const int rows = kWide ? E : (E + 1) >> 1;
+  for (int i = threadIdx.x; i < (rows + 1) * kHistThreads; i += blockDim.x) cnt[i] = 0u;
   __syncthreads();
   pdl_wait();
   pdl_launch_dependents();
-  unsigned short* mine = cnt + threadIdx.x;
+  const uint32_t mine = static_cast<uint32_t>(__cvta_generic_to_shared(cnt + threadIdx.x));
+  const unsigned int dump = kWide ? static_cast<unsigned int>(rows) : 2u * static_cast<unsigned int>(rows);
   const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
   const bool aligned = (reinterpret_cast<uintptr_t>(idx) & 15) == 0;
   const long long nvec = aligned ? (n >> 3) : 0;  // 8 labels per 16-byte load
   const int4* v4 = reinterpret_cast<const int4*>(idx);
-  auto add = [&](int v) {
-    if (v >= 0 && v < E) mine[v * kHistThreads] += 1;
+  // a label as an unsigned 16-bit value: negative labels (padding) are >= 32768 > E and land in the dump row
+  auto add = [&](unsigned int v) {
+    const unsigned int e = min(v, dump);
+    uint32_t addr, inc;
+    if constexpr (kWide) {
+      addr = mine + e * (kHistThreads * 4u);
+      inc = 1u;
+    } else {
+      addr = mine + (e & ~1u) * (kHistThreads * 2u);
+      inc = (e & 1u) * 0xffffu + 1u;
+    }
+    uint32_t c;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(c) : "r"(addr) : "memory");
+    c += inc;
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(c) : "memory");
   };
   auto add8 = [&](const int4& q) {
-    const int wv[4] = {q.x, q.y, q.z, q.w};
+    const unsigned int wv[4] = {static_cast<unsigned int>(q.x), static_cast<unsigned int>(q.y), static_cast<unsigned int>(q.z),
+                                static_cast<unsigned int>(q.w)};
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      add(static_cast<int16_t>(wv[c] & 0xffff));
-      add(static_cast<int16_t>((wv[c] >> 16) & 0xffff));
+      add(wv[c] & 0xffffu);
+      add(wv[c] >> 16);
     }
   };
-  auto fold = [&]() {
-    __syncthreads();
-    for (int e = threadIdx.x; e < E; e += blockDim.x) {
-      unsigned int tot = 0;
-      const unsigned int* row = reinterpret_cast<const unsigned int*>(cnt + e * kHistThreads);
-      // rotate the start so that the threads of a warp (consecutive experts) read different banks
-      for (int i = 0; i < kHistThreads / 2; ++i) {
-        const unsigned int w = row[(i + e) & (kHistThreads / 2 - 1)];
-        tot += (w & 0xffffu) + (w >> 16);
-      }
-      if (tot) atomicAdd(hist + e, static_cast<unsigned long long>(tot));
-    }
-    __syncthreads();
-  };
+  // software-pipelined: the next four 16-byte loads of a thread are in flight while it counts the current 32 labels
+  // (counting is a serial load / add / store chain of ~40 cycles per label: without the prefetch a thread had no load
+  // outstanding for 40 % of its time)
   long long i = tid;
-  for (; i + 3 * nthreads < nvec; i += 4 * nthreads) {     // four loads in flight per thread
-    int4 q[4];
+  int4 q[4];
+  bool have = i + 3 * nthreads < nvec;
+  if (have) {
 #pragma unroll
     for (int u = 0; u < 4; ++u) q[u] = __ldg(v4 + i + u * nthreads);
+  }
+  while (have) {
+    const long long i_next = i + 4 * nthreads;
+    const bool have_next = i_next + 3 * nthreads < nvec;
+    int4 qn[4];
+    if (have_next) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) qn[u] = __ldg(v4 + i_next + u * nthreads);
+    }
 #pragma unroll
     for (int u = 0; u < 4; ++u) add8(q[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) q[u] = qn[u];
+    i = i_next;
+    have = have_next;
   }
   for (; i < nvec; i += nthreads) add8(__ldg(v4 + i));
-  for (long long j = (nvec << 3) + tid; j < n; j += nthreads) add(static_cast<int>(idx[j]));
-  fold();
+  for (long long j = (nvec << 3) + tid; j < n; j += nthreads) add(static_cast<unsigned int>(static_cast<unsigned short>(idx[j])));
+  // fold: one thread per expert sums the 128 thread-private counters of its row
+  __syncthreads();
+  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+    unsigned int tot = 0;
+    const unsigned int* row = cnt + (kWide ? e : (e >> 1)) * kHistThreads;
+    const int sh = kWide ? 0 : ((e & 1) << 4);
+    const unsigned int msk = kWide ? 0xffffffffu : 0xffffu;
+    // rotate the start so that the threads of a warp (consecutive experts) spread over the banks
+    for (int j = 0; j < kHistThreads; ++j) tot += (row[(j + e) & (kHistThreads - 1)] >> sh) & msk;
+    if (tot) atomicAdd(hist + e, static_cast<unsigned long long>(tot));
+  }
 }
 
 // ------------------------------------------------------------------ column max over tokens
@@ -641,19 +679,25 @@ int moe_hist_accumulate(const int16_t* idx, long long n, int E, unsigned long lo
   if (n == 0) return MOE_OK;
   MOE_REQUIRE(idx != nullptr && hist != nullptr, MOE_ERR_INVALID_ARGUMENT, "moe_hist_accumulate: NULL pointer");
   MOE_REQUIRE(E <= 768, MOE_ERR_UNSUPPORTED_SHAPE, "moe_hist_accumulate: E=%d > 768 bins (thread-private counters exceed shared memory)", E);
-  const size_t smem = static_cast<size_t>(E) * kHistThreads * sizeof(unsigned short);
-  int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(hist_accumulate_kernel), smem);
+  const bool wide = E <= kHistWideMaxE;
+  const size_t smem = static_cast<size_t>((wide ? E : (E + 1) / 2) + 1) * kHistThreads * sizeof(unsigned int);
+  const void* kfn = wide ? reinterpret_cast<const void*>(hist_accumulate_kernel<true>)
+                         : reinterpret_cast<const void*>(hist_accumulate_kernel<false>);
+  int rc = ensure_dynamic_smem(kfn, smem);
   if (rc) return rc;
   const long long per_cta = static_cast<long long>(kHistThreads) * 8 * 8;  // 8 vector loads of 8 labels per thread
   long long ctas = (n + per_cta - 1) / per_cta;
   const int per_sm = smem > 0 ? static_cast<int>((200 * 1024) / smem) : 16;
   const long long max_ctas = static_cast<long long>(sm_count()) * (per_sm < 1 ? 1 : (per_sm > 16 ? 16 : per_sm));
   if (ctas > max_ctas) ctas = max_ctas;
-  const long long min_ctas = (n + static_cast<long long>(kHistThreads) * kHistMaxPerThread - 1) / (static_cast<long long>(kHistThreads) * kHistMaxPerThread);
-  if (ctas < min_ctas) ctas = min_ctas;       // 16-bit thread-private counters: bound the labels per thread
+  // 16-bit thread-private counters (packed layout): bound the labels per thread; 32-bit ones hold any count a launch can reach
+  const long long min_ctas = wide ? 1 : (n + static_cast<long long>(kHistThreads) * kHistMaxPerThread - 1) / (static_cast<long long>(kHistThreads) * kHistMaxPerThread);
+  if (ctas < min_ctas) ctas = min_ctas;
   MOE_REQUIRE(ctas <= 0x7fffffffLL, MOE_ERR_UNSUPPORTED_SHAPE, "moe_hist_accumulate: n=%lld too large", n);
-  cudaError_t le = launch_pdl(hist_accumulate_kernel, dim3(static_cast<unsigned>(ctas)), dim3(kHistThreads), smem,
-                              static_cast<cudaStream_t>(stream), idx, n, E, hist);
+  cudaError_t le = wide ? launch_pdl(hist_accumulate_kernel<true>, dim3(static_cast<unsigned>(ctas)), dim3(kHistThreads), smem,
+                                     static_cast<cudaStream_t>(stream), idx, n, E, hist)
+                        : launch_pdl(hist_accumulate_kernel<false>, dim3(static_cast<unsigned>(ctas)), dim3(kHistThreads), smem,
+                                     static_cast<cudaStream_t>(stream), idx, n, E, hist);
   if (le != cudaSuccess) return fail(MOE_ERR_CUDA, "moe_hist_accumulate launch: %s", cudaGetErrorString(le));
   return check_launch("moe_hist_accumulate");
 }
