@@ -81,7 +81,8 @@ constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kNumThreads = kEpiWarp0 * 32 + kEpiThreads;
 constexpr int kMaxStages = 12;
 constexpr int kSmemLimit = 232448;
-constexpr int kBiasBytesPerWarp = 128 * 4;          // 2 x 64 floats
+constexpr int kBiasBytesPerWarp = 64 * 4;           // phase 1: 32 value + 32 gate biases (cpg <= 32), phase 3: up to 64 output biases
+constexpr int kBiasGateOff = 32;
 constexpr int kSpartPerRow = 8;                      // partial / per-expert score slots per token row and tile
 constexpr int kMaxWords = 8;                         // expert-set words per token (E <= 256)
 constexpr int kMaxExperts = 32 * kMaxWords;
@@ -143,6 +144,9 @@ struct Shape {
   int words;                                    // expert-set words per token
   int act, mask_h, count_begin, count_end;
   int prefetch_weights;
+  int rev3;                                     // phase-3 items walk the row blocks from the last one down
+  int trace_p3;                                 // trace build only: the per-item stamps follow the phase-3 items
+  int hist_slots;                               // shared-memory histogram bins: E rounded up to a multiple of 32
   int pub_batch;                                // phase-1 tiles published per GPU-scope release (2 .. 4)
   uint32_t es_magic;
 };
@@ -327,8 +331,9 @@ __device__ __forceinline__ bool item3(const Shape& g, int it, int p, int P, int 
   if (j >= g.items3) return false;
   t.slice = j % g.split3;
   const int r = j / g.split3;
-  const int mp = r / g.n_tiles3;
+  int mp = r / g.n_tiles3;
   t.n = r - mp * g.n_tiles3;
+  if (g.rev3) mp = g.m_pairs - 1 - mp;      // last-written row blocks first: their H tiles are still in L2
   t.m_blk = 2 * mp + rm;
   t.kb_begin = t.slice * g.kb_per_slice3;
   t.kb_end = min(g.nkb3, t.kb_begin + g.kb_per_slice3);
@@ -363,11 +368,14 @@ struct Tile1Iter {
 
 // ------------------------------------------------------------------------------------------ the kernel
 // per-warp bias slices staged in shared memory: lanes load coalesced, everyone re-reads float4 broadcasts
-__device__ __forceinline__ void stage_bias(float* sb, const float* b0, const float* b1, int n, int lane) {
+// (phase 1: n <= 32 value biases at sb[0 ..] and the gate biases at sb[kBiasGateOff ..]; phase 3: n <= 64 biases at sb[0 ..])
+__device__ __forceinline__ void stage_bias(float* sb, const float* b0, const float* b1, int n, int lane, bool two_halves) {
   __syncwarp();
-  for (int i = lane; i < 64; i += 32) {
-    sb[i] = (b0 != nullptr && i < n) ? __ldg(b0 + i) : 0.f;
-    sb[64 + i] = (b1 != nullptr && i < n) ? __ldg(b1 + i) : 0.f;
+  if (two_halves) {
+    sb[lane] = (b0 != nullptr && lane < n) ? __ldg(b0 + lane) : 0.f;
+    sb[kBiasGateOff + lane] = (b1 != nullptr && lane < n) ? __ldg(b1 + lane) : 0.f;
+  } else {
+    for (int i = lane; i < 64; i += 32) sb[i] = (b0 != nullptr && i < n) ? __ldg(b0 + i) : 0.f;
   }
   __syncwarp();
 }
@@ -501,7 +509,7 @@ __device__ __forceinline__ void geglu_group(uint32_t taddr_v, uint32_t taddr_g, 
         if (i == kA) tc::tmem_ld_wait();
       }
       const float4 bv = *reinterpret_cast<const float4*>(sbias + c + i);
-      const float4 bg = *reinterpret_cast<const float4*>(sbias + 64 + c + i);
+      const float4 bg = *reinterpret_cast<const float4*>(sbias + kBiasGateOff + c + i);
       float ga, gb, gc, gd;
       unpk2(add2(pk2(__uint_as_float(gt[i]), __uint_as_float(gt[i + 1])), pk2(bg.x, bg.y)), ga, gb);
       unpk2(add2(pk2(__uint_as_float(gt[i + 2]), __uint_as_float(gt[i + 3])), pk2(bg.z, bg.w)), gc, gd);
@@ -554,8 +562,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   float* sbias_all = reinterpret_cast<float*>(smem + g.tail_off);
   float* spart = sbias_all + kEpiWarps * (kBiasBytesPerWarp / 4);             // [2][128][kSpartPerRow], or empty
   uint32_t* s_words_all = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(spart) + g.spart_bytes);   // [16 warps][16]: tokens per warp x words
-  unsigned int* s_hist = s_words_all + kEpiWarps * 16;                        // [kMaxExperts]
-  Barriers* bars = reinterpret_cast<Barriers*>(s_hist + kMaxExperts);
+  unsigned int* s_hist = s_words_all + kEpiWarps * 16;                        // [g.hist_slots] (E rounded up to 32)
+  Barriers* bars = reinterpret_cast<Barriers*>(s_hist + g.hist_slots);
 
   const int rm = static_cast<int>(tc::cluster_ctarank());
   const int p = static_cast<int>(blockIdx.x) >> 1, P = static_cast<int>(gridDim.x) >> 1;
@@ -592,7 +600,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       tc::prefetch_tensormap(&tmap_y_rem);
     }
   }
-  for (int i = threadIdx.x; i < kMaxExperts; i += kNumThreads) s_hist[i] = 0u;
+  for (int i = threadIdx.x; i < g.hist_slots; i += kNumThreads) s_hist[i] = 0u;
   tc::fence_before_thread_sync();
   __syncthreads();
   tc::cluster_sync_all();
@@ -662,6 +670,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             poll_at_least(ws_rec + t.m_blk * kBlockRecInts + 1, g.chunks_per_block);
 #if MOE_TRACE
             if (it == 0) TRACE(63);
+            if (g.trace_p3 && it < 8) TRACE(48 + it);
 #endif
           }
           __syncwarp();
@@ -686,13 +695,13 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         }
         for (int kb = t.kb_begin; kb < t.kb_end; kb += ks) {
 #if MOE_TRACE
-          if (do_a && lane == 0 && phase == 0 && it == 4 && kb == t.kb_begin && g.items1 > 5 * P) TRACE(54);
-          if (do_a && lane == 0 && phase == 1 && it == 0 && kb == t.kb_begin && g.items1 <= 5 * P) TRACE(54);
+          if (!g.trace_p3 && do_a && lane == 0 && phase == 0 && it == 4 && kb == t.kb_begin && g.items1 > 5 * P) TRACE(54);
+          if (!g.trace_p3 && do_a && lane == 0 && phase == 1 && it == 0 && kb == t.kb_begin && g.items1 <= 5 * P) TRACE(54);
 #endif
           tc::mbar_wait(&empty_bar[s], ph ^ 1u);
 #if MOE_TRACE
-          if (do_a && lane == 0 && phase == 0 && it == 4 && kb + ks >= t.kb_end && g.items1 > 5 * P) TRACE(55);
-          if (do_a && lane == 0 && phase == 1 && it == 0 && kb + ks >= t.kb_end && g.items1 <= 5 * P) TRACE(55);
+          if (!g.trace_p3 && do_a && lane == 0 && phase == 0 && it == 4 && kb + ks >= t.kb_end && g.items1 > 5 * P) TRACE(55);
+          if (!g.trace_p3 && do_a && lane == 0 && phase == 1 && it == 0 && kb + ks >= t.kb_end && g.items1 <= 5 * P) TRACE(55);
 #endif
           uint8_t* sa = ring + s * slot_bytes;
           uint8_t* sb = res1 ? sa : sa + ks * kABytes;
@@ -783,22 +792,22 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             last_of_run = !it1.valid() || it1.mp != cur_mp;
           }
 #if MOE_TRACE
-          if (lane == 0 && acc_it == 4 && g.items1 > 5 * P) TRACE(50);
-          if (lane == 0 && phase == 1 && it == 0 && g.items1 <= 5 * P) TRACE(50);
+          if (!g.trace_p3 && lane == 0 && acc_it == 4 && g.items1 > 5 * P) TRACE(50);
+          if (!g.trace_p3 && lane == 0 && phase == 1 && it == 0 && g.items1 <= 5 * P) TRACE(50);
 #endif
           tc::mbar_wait(&bars->tmem_empty[as], ((acc_it >> 1) & 1u) ^ 1u);
           tc::fence_after_thread_sync();
 #if MOE_TRACE
-          if (lane == 0 && acc_it == 4 && g.items1 > 5 * P) TRACE(51);
-          if (lane == 0 && phase == 1 && it == 0 && g.items1 <= 5 * P) TRACE(51);
+          if (!g.trace_p3 && lane == 0 && acc_it == 4 && g.items1 > 5 * P) TRACE(51);
+          if (!g.trace_p3 && lane == 0 && phase == 1 && it == 0 && g.items1 <= 5 * P) TRACE(51);
 #endif
           const uint32_t d_tmem = tb + as * kAccStride;
           for (int kb = t.kb_begin; kb < t.kb_end; kb += ks) {
             tc::mbar_wait(&full_bar[s], ph);
             tc::fence_after_thread_sync();
 #if MOE_TRACE
-            if (lane == 0 && acc_it == 4 && g.items1 > 5 * P) TRACE(kb == t.kb_begin ? 52 : 53);
-            if (lane == 0 && phase == 1 && it == 0 && g.items1 <= 5 * P) TRACE(kb == t.kb_begin ? 52 : 53);
+            if (!g.trace_p3 && lane == 0 && acc_it == 4 && g.items1 > 5 * P) TRACE(kb == t.kb_begin ? 52 : 53);
+            if (!g.trace_p3 && lane == 0 && phase == 1 && it == 0 && g.items1 <= 5 * P) TRACE(kb == t.kb_begin ? 52 : 53);
 #endif
             const uint32_t slot = ring + s * slot_bytes;
             const uint32_t a_base = res1 ? a_res + static_cast<uint32_t>(kb) * kABytes : slot;
@@ -831,7 +840,10 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             tc::umma_commit_2sm_mc(&bars->tmem_full[as], 0x3);   // accumulator complete -> both epilogues
             if (last_of_run) tc::umma_commit_2sm_mc(&bars->a_empty, 0x3);   // the resident panels may be replaced
 #if MOE_TRACE
-            if (acc_it < 8) TRACE(8 + 4 * acc_it);
+            {
+              const int tix = g.trace_p3 ? (phase == 1 ? it : 99) : acc_it;
+              if (tix < 8) TRACE(8 + 4 * tix);
+            }
 #endif
           }
           __syncwarp();
@@ -863,7 +875,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         const int buf = st_it & 1;
         tc::mbar_wait(&bars->hs_full[buf], use_p1[buf] & 1u);
 #if MOE_TRACE
-        if (lane == 0 && it >= 2 && it < 4) TRACE(40 + 4 * (it - 2));
+        if (!g.trace_p3 && lane == 0 && it >= 2 && it < 4) TRACE(40 + 4 * (it - 2));
 #endif
         if (lane == 0 && !g.direct_h) {   // (direct-H mode: the epilogue threads have already stored the tile)
           const uint8_t* src = hstage + buf * g.hs_bytes;
@@ -894,7 +906,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           tc::tma_store_wait_read<0>();
           tc::mbar_arrive(&bars->hs_empty[buf]);   // the epilogue warps may refill the buffer
 #if MOE_TRACE
-          if (it >= 2 && it < 4) TRACE(41 + 4 * (it - 2));
+          if (!g.trace_p3 && it >= 2 && it < 4) TRACE(41 + 4 * (it - 2));
 #endif
           Item nx;
           if (n_pend >= g.pub_batch - 1 && item1(g, it + 1, p, P, rm, nx)) {
@@ -907,9 +919,9 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
               if (i < n_pend) atomicAdd(ws_rec + pend[i] * kBlockRecInts, 1);
             n_pend = 0;
 #if MOE_TRACE
-            if (it >= 2 && it < 4) TRACE(42 + 4 * (it - 2));
-            if (st_it - 1 < 8) TRACE(8 + 4 * (st_it - 1) + 3);
-            if (it >= 2 && it < 4) TRACE(43 + 4 * (it - 2));
+            if (!g.trace_p3 && it >= 2 && it < 4) TRACE(42 + 4 * (it - 2));
+            if (!g.trace_p3 && st_it - 1 < 8) TRACE(8 + 4 * (st_it - 1) + 3);
+            if (!g.trace_p3 && it >= 2 && it < 4) TRACE(43 + 4 * (it - 2));
 #endif
           }
 #pragma unroll
@@ -930,7 +942,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         for (int i = 0; i < kPubBatch; ++i)
           if (i < n_pend) atomicAdd(ws_rec + pend[i] * kBlockRecInts, 1);
 #if MOE_TRACE
-        if (st_it - 1 < 8) TRACE(8 + 4 * (st_it - 1) + 3);
+        if (!g.trace_p3 && st_it - 1 < 8) TRACE(8 + 4 * (st_it - 1) + 3);
 #endif
       }
       __syncwarp();
@@ -1032,7 +1044,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       // the previous tile is being processed (a staged load per tile exposed ~0.8 us of global latency each time)
       if (i1 < n_items1)
         stage_bias(sbias, a.b1 != nullptr ? a.b1 + n1 * nv + col0 : nullptr,
-                   a.b1 != nullptr ? a.b1 + g.h + n1 * nv + col0 : nullptr, cpg, lane);
+                   a.b1 != nullptr ? a.b1 + g.h + n1 * nv + col0 : nullptr, cpg, lane, true);
       int it = 0;
       for (; i1 < n_items1; ++it, ++acc_it) {
         const int mp_cur = mp1, n_cur = n1;
@@ -1065,7 +1077,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         tc::mbar_wait(&bars->tmem_full[as], (acc_it >> 1) & 1u);
         tc::fence_after_thread_sync();
 #if MOE_TRACE
-        if (ew == 0 && lane == 0 && acc_it < 8) TRACE(8 + 4 * acc_it + 1);
+        if (!g.trace_p3 && ew == 0 && lane == 0 && acc_it < 8) TRACE(8 + 4 * acc_it + 1);
 #endif
         // (the alignment of the group's staging stores is warp-uniform: two instantiations, one uniform branch)
 #define MOE_GEGLU_CALL(ACT_, AL_, DIR_) \
@@ -1096,14 +1108,14 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         if (lane == 0) tc::mbar_arrive_cluster(tc::mapa_u32(&bars->tmem_empty[as], 0));
         if (has_next) {   // this warp is done reading the current slices
           sbias[lane] = nb0;
-          sbias[64 + lane] = nb2;
+          sbias[kBiasGateOff + lane] = nb2;
         }
         // H tile: generic-proxy smem writes -> async proxy; the sync warp stores it and publishes the tile
         if (!direct_h) tc::fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&bars->hs_full[buf]);
 #if MOE_TRACE
-        if (ew == 0 && lane == 0 && acc_it < 8) TRACE(8 + 4 * acc_it + 2);
+        if (!g.trace_p3 && ew == 0 && lane == 0 && acc_it < 8) TRACE(8 + 4 * acc_it + 2);
 #endif
       }
       use0 = (it + 1) >> 1;
@@ -1119,6 +1131,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         tc::mbar_wait(&bars->route_req, idx & 1u);
 #if MOE_TRACE
         if (ew == 0 && lane == 0 && idx == 0) TRACE(60);
+        if (g.trace_p3 && ew == 0 && lane == 0 && idx < 8) TRACE(40 + idx);
 #endif
         // per chunk: select -> zero-writes -> (after the item's last chunk) signal -> labels / histogram.  The signal
         // follows a __syncwarp: every lane's zero-writes precede lane 0's arrive (release at CTA scope; the sync warp's
@@ -1129,6 +1142,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           if (lane == 0) tc::mbar_arrive(&bars->route_done);
 #if MOE_TRACE
           if (ew == 0 && lane == 0) TRACE(61);
+          if (g.trace_p3 && ew == 0 && lane == 0 && idx < 8) TRACE(8 + 4 * idx + 3);
 #endif
         };
         if (c0 >= g.chunks_per_block) {       // more consumers than chunks: nothing to route for this item
@@ -1148,7 +1162,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         }
         const int n0 = t.n * g.bn + col0;                  // first output column of this warp's group
         const int nvalid = max(0, min(cpg, g.d - n0));     // the last tile may overhang d
-        stage_bias(sbias, a.b2 != nullptr ? a.b2 + n0 : nullptr, nullptr, nvalid, lane);
+        stage_bias(sbias, a.b2 != nullptr ? a.b2 + n0 : nullptr, nullptr, nvalid, lane, false);
         if (g.split3 == 1) {
           // the whole staging area (both phase-1 buffers) holds one Y tile
           if (use0 > 0) tc::mbar_wait(&bars->hs_empty[0], (use0 - 1) & 1u);
@@ -1157,7 +1171,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         tc::mbar_wait(&bars->tmem_full[as], (acc_it >> 1) & 1u);
         tc::fence_after_thread_sync();
 #if MOE_TRACE
-        if (ew == 0 && lane == 0 && acc_it < 8) TRACE(8 + 4 * acc_it + 1);
+        if (ew == 0 && lane == 0 && (g.trace_p3 ? it : acc_it) < 8) TRACE(8 + 4 * (g.trace_p3 ? it : acc_it) + 1);
 #endif
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + as * kAccStride + col0;
         const int row = t.m_blk * kBlockM + q_row;
@@ -1206,7 +1220,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           __syncwarp();
           if (lane == 0) tc::mbar_arrive_cluster(tc::mapa_u32(&bars->tmem_empty[as], 0));
 #if MOE_TRACE
-          if (ew == 0 && lane == 0 && it == 0) TRACE(48);
+          if (!g.trace_p3 && ew == 0 && lane == 0 && it == 0) TRACE(48);
 #endif
           // all partial stores of the CTA, then ONE releasing increment: it publishes this slice's partial tile; the
           // last slice to arrive reads the other slices' tiles from L2 (ld.cg) after the barrier below.  (Letting every
@@ -1222,7 +1236,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           }
           tc::named_bar_sync(1, kEpiThreads);
 #if MOE_TRACE
-          if (ew == 0 && lane == 0 && it == 0) TRACE(49);
+          if (!g.trace_p3 && ew == 0 && lane == 0 && it == 0) TRACE(49);
 #endif
           if (bars->last_cta) {
             // sum the slices (row index fastest: coalesced 16-byte loads), add b2, and stage the bf16 tile in the
@@ -1295,7 +1309,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           tc::named_bar_sync(1, kEpiThreads);
         }
 #if MOE_TRACE
-        if (ew == 0 && lane == 0 && acc_it < 8) TRACE(8 + 4 * acc_it + 2);
+        if (ew == 0 && lane == 0 && (g.trace_p3 ? it : acc_it) < 8) TRACE(8 + 4 * (g.trace_p3 ? it : acc_it) + 2);
 #endif
       }
     }
@@ -1480,7 +1494,7 @@ int moe_ffn_fused(const void* x, const void* w1p, const float* b1p, const void* 
   for (int cand = 128; cand >= 16; cand -= 8) {
     if (h % cand) continue;
     const int cpg = cand / 4;
-    if (cpg % 4 || cpg > 64) continue;
+    if (cpg % 4 || cpg > 32) continue;
     const bool whole = cpg % es == 0;
     const bool spans = es % cpg == 0 && (es / cpg == 2 || es / cpg == 4) && cand % es == 0;
     if (!(whole || spans)) continue;
@@ -1569,7 +1583,8 @@ int moe_ffn_fused(const void* x, const void* w1p, const float* b1p, const void* 
   // ---- pipeline: k-blocks per stage (2 if at least 3 stages fit), ring slot = the larger of the two phases
   g.hs_bytes = kBlockM * nv * 2;
   g.spart_bytes = (g.chunks_per_expert == 0) ? 2 * kBlockM * kSpartPerRow * 4 : 0;   // only experts that span column groups
-  const int small = kEpiWarps * kBiasBytesPerWarp + g.spart_bytes + kEpiWarps * 16 * 4 + kMaxExperts * 4 +
+  g.hist_slots = (E + 31) / 32 * 32;
+  const int small = kEpiWarps * kBiasBytesPerWarp + g.spart_bytes + kEpiWarps * 16 * 4 + g.hist_slots * 4 +
                     static_cast<int>(sizeof(Barriers)) + 64;
   const int fixed = 1024 + 2 * g.hs_bytes + small;
   int ks = 2;
@@ -1608,6 +1623,10 @@ int moe_ffn_fused(const void* x, const void* w1p, const float* b1p, const void* 
     const int region = (kSmemLimit - fixed) / 1024 * 1024;
     int ares_ks = g.ks1;
     if (const char* e = getenv("MOE_FUSED_ARES_KS")) ares_ks = atoi(e) == 1 ? 1 : g.ks1;
+    // MOE_FUSED_ARES=2: whole-tile slots (one barrier round trip and one commit per tile, two tiles of W1 in flight)
+    if (const char* e = getenv("MOE_FUSED_ARES")) {
+      if (atoi(e) == 2) ares_ks = g.nkb1;
+    }
     const int slot1 = ares_ks * nv * 128;
     int stages1 = (region - g.a_res_bytes) / slot1;
     if (stages1 > kMaxStages) stages1 = kMaxStages;
@@ -1693,10 +1712,15 @@ int moe_ffn_fused(const void* x, const void* w1p, const float* b1p, const void* 
   g.count_begin = count_begin;
   g.count_end = count_end;
   g.es_magic = static_cast<uint32_t>((0x100000000ull / static_cast<unsigned>(es)) + 1ull);
+  g.trace_p3 = getenv("MOE_TRACE_P3") != nullptr ? 1 : 0;
   g.prefetch_weights = 1;
   if (const char* e = getenv("MOE_FUSED_PREFETCH")) g.prefetch_weights = atoi(e) != 0;
   // tiles published per release: pairs with few tiles publish each one (early finishers start routing the early blocks),
   // pairs with many amortise the fence (measured: profiles/r02_sweep_publication_batch.log)
+  // H larger than L2 (UNet batch 16 at d = 320: 168 MB): phase 1 leaves only the most recently written row blocks in L2;
+  // phase 3 then starts with those, so that the routing stage's partial-sector zero stores and the first H loads hit L2
+  g.rev3 = static_cast<size_t>(T) * h * 2 > (static_cast<size_t>(96) << 20) ? 1 : 0;
+  if (const char* e = getenv("MOE_FUSED_REV3")) g.rev3 = atoi(e) != 0;
   g.pub_batch = (g.items1 >= 6 * P) ? 4 : 2;
   if (const char* e = getenv("MOE_FUSED_PUB")) {
     const int v = atoi(e);

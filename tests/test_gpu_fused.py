@@ -164,17 +164,18 @@ def test_fused_repeat_launches_share_workspace(lib):
     assert int(ws[:sync_bytes].view(torch.int32).abs().sum()) == 0
 
 
-@pytest.mark.parametrize("env", ["MOE_FUSED_ARES", "MOE_FUSED_DIRECT"])
+@pytest.mark.parametrize("env,val", [("MOE_FUSED_ARES", "1"), ("MOE_FUSED_ARES", "2"), ("MOE_FUSED_DIRECT", "1")])
 @pytest.mark.parametrize("d,h,shape,es", [(320, 1280, (2, 2500), 20), (128, 640, (1, 9600), 20), (64, 256, (5, 4000), 16),
                                           (640, 2560, (1, 700), 20)])
-def test_fused_experimental_schedules_are_bit_identical(lib, monkeypatch, env, d, h, shape, es):
+def test_fused_experimental_schedules_are_bit_identical(lib, monkeypatch, env, val, d, h, shape, es):
     """The two experimental phase-1 schedules (off by default) give the same bits as the default:
     MOE_FUSED_ARES=1 -- contiguous runs of column tiles per CTA pair with the row block's x panels resident in shared
-    memory; MOE_FUSED_DIRECT=1 -- H rows stored straight from the epilogue threads, the staging space used as ring slots.
+    memory (=2: whole-tile W1 slots, one barrier round trip per tile); MOE_FUSED_DIRECT=1 -- H rows stored straight from the
+    epilogue threads, the staging space used as ring slots.
     Both put phase 1 on its own ring and re-carve shared memory for phase 3; ragged last row block included."""
     layer = O.synthetic_layer(d, h, shape, es, seed=11)
     ref = fused_layer(layer, 0.3)
-    monkeypatch.setenv(env, "1")
+    monkeypatch.setenv(env, val)
     res = fused_layer(layer, 0.3, repeats=2)
     for key in ("scores", "idx", "H", "y", "hist"):
         assert torch.equal(ref[key], res[key]), key

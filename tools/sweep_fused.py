@@ -61,7 +61,11 @@ for d, T in shapes:
         for s in sets:
             torch.matmul(s["x"], s["w1"].t()); torch.matmul(s["H"], s["w2"].t())
 
-    tf, ts, tc_ = timed(fused), timed(split), timed(cublas)
     fl = 6.0 * d * h * T
+    if os.environ.get("FUSED_ONLY"):
+        tf = timed(fused)
+        print(f"d={d} T={T} es={ES}: fused {tf:6.1f}us ({fl/tf/1e6:5.0f} TF)", flush=True)
+        continue
+    tf, ts, tc_ = timed(fused), timed(split), timed(cublas)
     print(f"d={d} T={T} es={ES}: fused {tf:6.1f}us ({fl/tf/1e6:5.0f} TF) | split {ts:6.1f}us ({fl/ts/1e6:5.0f} TF) | "
           f"cuBLAS GEMMs only {tc_:6.1f}us ({fl/tc_/1e6:5.0f} TF)", flush=True)

@@ -30,6 +30,15 @@ def show(name, tr, ms):
         return f"{c.min():6.2f}/{c.median():6.2f}/{c.max():6.2f} ({len(c):3d})" if len(c) else "     -"
     print(f"{name}: {ms*1e3:7.1f}us event-timed, {tr.shape[0]} CTAs; min/median/max over CTAs (n), us since first CTA entry")
     print(f"   entry {col(0)} | setup {col(1)} | pdl_wait {col(2)} | first TMA {col(7)} | first MMA {col(3)}")
+    if os.environ.get("MOE_TRACE_P3"):
+        # per-item stamps follow the PHASE-3 items: route begin / end (epilogue warps), block ready at the A producer,
+        # MMA commit, epilogue begin / done
+        for it in range(8):
+            b = 8 + 4 * it
+            print(f"   p3 item {it}: route begin {col(40+it)} | route end {col(b+3)} | ready seen {col(48+it)} | mma-commit {col(b)} | "
+                  f"epi-begin {col(b+1)} | epi-done {col(b+2)}")
+        print(f"   A-producer reaches first ready-wait {col(62)} | epi all done {col(4)} | exit {col(6)}")
+        return
     for it in range(8):
         b = 8 + 4 * it
         if torch.isnan(rel[:, b]).all() and torch.isnan(rel[:, b + 1]).all():
