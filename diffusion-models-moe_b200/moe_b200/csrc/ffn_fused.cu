@@ -661,6 +661,9 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       }
       int cur_mp = -1, a_runs = 0;
       for (int it = 0; phase == 0 ? item1(g, it, p, P, rm, t) : item3(g, it, p, P, rm, t); ++it) {
+#if MOE_TRACE
+        if (!g.trace_p3 && g.split3 == 1 && do_a && lane == 0 && phase == 0 && it == 0) TRACE(48);   // ramp: first item known (slot shared with the split-K stamps)
+#endif
         if (phase == 1 && do_a) {
           // the block's H rows are complete and routed once every routing chunk of the block has been counted
           if (lane == 0) {
@@ -699,6 +702,9 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           if (!g.trace_p3 && do_a && lane == 0 && phase == 1 && it == 0 && kb == t.kb_begin && g.items1 <= 5 * P) TRACE(54);
 #endif
           tc::mbar_wait(&empty_bar[s], ph ^ 1u);
+#if MOE_TRACE
+          if (!g.trace_p3 && g.split3 == 1 && do_a && lane == 0 && phase == 0 && it == 0 && kb == 0) TRACE(49);   // ramp: first slot wait passed
+#endif
 #if MOE_TRACE
           if (!g.trace_p3 && do_a && lane == 0 && phase == 0 && it == 4 && kb + ks >= t.kb_end && g.items1 > 5 * P) TRACE(55);
           if (!g.trace_p3 && do_a && lane == 0 && phase == 1 && it == 0 && kb + ks >= t.kb_end && g.items1 <= 5 * P) TRACE(55);

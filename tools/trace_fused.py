@@ -48,7 +48,7 @@ def show(name, tr, ms):
     for i in range(2):
         print(f"   sync warp, tile {i+2}: hs_full seen {col(40+4*i)} | stores read, buffer released {col(41+4*i)} | "
               f"previous tile's stores complete {col(42+4*i)} | previous tile published {col(43+4*i)}")
-    print(f"   split-K epilogue (first phase-3 item): partials stored {col(48)} | counted {col(49)}")
+    print(f"   split-K epilogue (first phase-3 item): partials stored {col(48)} | counted {col(49)}   (without split-K: A producer knows its first tile | past its first slot wait)")
     def d(i, j):
         c = rel[:, j] - rel[:, i]; c = c[~torch.isnan(c)]
         return f"{c.min():5.2f}/{c.median():5.2f}/{c.max():5.2f}" if len(c) else "-"
