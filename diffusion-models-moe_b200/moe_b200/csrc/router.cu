@@ -613,8 +613,12 @@ int moe_router_topk_biased(const float* scores, const float* score_bias, const u
   a.es_magic = es >= 1 ? static_cast<uint32_t>((0x100000000ull / static_cast<unsigned>(es)) + 1ull) : 0u;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   cudaError_t le = cudaSuccess;
-  const char* legacy_env = getenv("MOE_ROUTER_LEGACY");       // tests / A-B timing: force the warp-per-token kernel
-  const bool legacy = legacy_env != nullptr && atoi(legacy_env) != 0;
+  // Which kernel: the several-tokens-per-warp kernel needs enough tokens to fill the machine (a CTA routes 16-64 tokens
+  // per pass with long in-register sorting networks: at the UNet-batch-2 shapes of the d >= 640 layers it launches 32-64
+  // CTAs and takes 13 us where the warp-per-token kernel takes 6; at T = 65 536 it is 2.5x faster; tie at T = 8192).
+  // MOE_ROUTER_LEGACY=1 / =0 force the warp-per-token / the several-tokens-per-warp kernel (tests, A-B timing).
+  const char* legacy_env = getenv("MOE_ROUTER_LEGACY");
+  const bool legacy = legacy_env != nullptr ? atoi(legacy_env) != 0 : T < 12288;
   const bool vec_ok = H == nullptr || (es % 4 == 0 && h % 8 == 0 && (reinterpret_cast<uintptr_t>(H) & 15) == 0);
   if (E <= 256 && vec_ok && !legacy) {
     // several tokens per warp (route.cuh): the smallest lane count per token that keeps <= 16 experts per lane
