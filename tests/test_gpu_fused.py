@@ -181,6 +181,23 @@ def test_fused_experimental_schedules_are_bit_identical(lib, monkeypatch, env, v
         assert torch.equal(ref[key], res[key]), key
 
 
+def test_fused_reversed_phase3_order_is_bit_identical(lib, monkeypatch):
+    """When H exceeds 96 MB (UNet batch 16 at d = 320) the phase-3 items walk the row blocks from the last-written one
+    down (their H tiles are still in L2); MOE_FUSED_REV3 forces the order either way.  Same arithmetic, same bits --
+    checked on a small ragged shape (forced) and on one large enough to switch by itself."""
+    for d, h, shape, es in [(320, 1280, (3, 1000), 20), (320, 1280, (1, 40100), 20)]:
+        layer = O.synthetic_layer(d, h, shape, es, seed=5)
+        monkeypatch.setenv("MOE_FUSED_REV3", "0")
+        ref = fused_layer(layer, 0.3)
+        monkeypatch.setenv("MOE_FUSED_REV3", "1")
+        rev = fused_layer(layer, 0.3, repeats=2)
+        monkeypatch.delenv("MOE_FUSED_REV3")
+        auto = fused_layer(layer, 0.3)
+        for key in ("scores", "idx", "H", "y", "hist"):
+            assert torch.equal(ref[key], rev[key]), key
+            assert torch.equal(ref[key], auto[key]), key
+
+
 def test_fused_without_masking_is_the_dense_ffn(lib):
     """mask_h=False (the ExpertPredictivity contract, expert_activation.py:62: statistics only, unmasked output): the
     routing outputs are unchanged, H and Y are those of the dense FFN."""
