@@ -201,6 +201,17 @@ def test_histogram_kernel(lib):
         assert torch.equal(hist.cpu(), torch.bincount(idx.long(), minlength=E))
         M.hist_accumulate(idx.to(DEV), E, hist)                     # accumulates
         assert torch.equal(hist.cpu(), 2 * torch.bincount(idx.long(), minlength=E))
+    # padding (-1) and out-of-range labels are ignored; odd and boundary bin counts (E = 64: one 32-bit counter per
+    # expert; E = 65, 101, 768: two 16-bit counters per word, the odd last expert alone in its word)
+    for n, E in [(50001, 64), (50001, 65), (70003, 101), (30000, 768)]:
+        g = torch.Generator().manual_seed(n + E)
+        idx = torch.randint(-3, E + 5, (n,), generator=g, dtype=torch.int16)
+        ok = (idx >= 0) & (idx < E)
+        assert torch.equal(M.hist_accumulate(idx.to(DEV), E).cpu(), torch.bincount(idx[ok].long(), minlength=E))
+    # one label repeated 12 M times: the 16-bit thread-private counters of the packed layout must not wrap
+    idx = torch.full((12_000_000,), 77, dtype=torch.int16, device=DEV)
+    hist = M.hist_accumulate(idx, 256).cpu()
+    assert int(hist[77]) == 12_000_000 and int(hist.sum()) == 12_000_000
     # unaligned view (scalar path) and empty input
     idx = torch.randint(0, 64, (1001,), dtype=torch.int16).to(DEV)
     assert torch.equal(M.hist_accumulate(idx[1:], 64).cpu(), torch.bincount(idx[1:].cpu().long(), minlength=64))
