@@ -683,7 +683,8 @@ int moe_hist_accumulate(const int16_t* idx, long long n, int E, unsigned long lo
   if (n == 0) return MOE_OK;
   MOE_REQUIRE(idx != nullptr && hist != nullptr, MOE_ERR_INVALID_ARGUMENT, "moe_hist_accumulate: NULL pointer");
   MOE_REQUIRE(E <= 768, MOE_ERR_UNSUPPORTED_SHAPE, "moe_hist_accumulate: E=%d > 768 bins (thread-private counters exceed shared memory)", E);
-  const bool wide = E <= kHistWideMaxE;
+  bool wide = E <= kHistWideMaxE;
+  if (const char* e = getenv("MOE_HIST_WIDE")) wide = atoi(e) != 0 && E <= 96;      // A-B timing
   const size_t smem = static_cast<size_t>((wide ? E : (E + 1) / 2) + 1) * kHistThreads * sizeof(unsigned int);
   const void* kfn = wide ? reinterpret_cast<const void*>(hist_accumulate_kernel<true>)
                          : reinterpret_cast<const void*>(hist_accumulate_kernel<false>);
